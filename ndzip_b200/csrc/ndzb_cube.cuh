@@ -1,0 +1,559 @@
+// ndzb_cube.cuh — per-thread building blocks of the hypercube codec.
+//
+// Everything here is __host__ __device__ and free of warp intrinsics, so the exact code the kernels
+// run can also be driven lane by lane from the CPU simulation in tests/host_sim (which checks it
+// bit for bit against the oracle without a GPU). The kernels in ndzb_compress.cu / ndzb_decompress.cu
+// add the CTA-level parts: TMA / global loads, scans, the decoupled look-back, barriers.
+//
+// Work decomposition (differs from the reference's one-warp-per-chunk scheme,
+// reference src/ndzip/cuda_codec.inl:204-274): a cube of 4096 elements is handled by 128 threads;
+// thread u owns "run" u = the 32 consecutive cube-local elements [32u, 32u+32) and
+//   * computes their Lorenzo residuals straight from shared memory (reads its own run plus the
+//     1 / 2 / 5 neighbouring half-runs the stencil needs) — no in-place multi-pass transform,
+//   * bit-transposes them in registers with a 5-stage butterfly (32x32 bits per thread),
+//   * writes the 32 bit planes to a staging tile from which a warp-per-chunk pass compacts the
+//     non-zero planes directly into the output stream.
+// float : run u == chunk u (32 values x 32 bits).
+// double: chunk c (64 values x 64 bits) == runs 2c, 2c+1; each thread transposes the high and the
+//         low words of its 32 values (two 32x32 transposes) and owns one 32-bit half of every plane.
+#pragma once
+
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define NDZB_HD __host__ __device__ __forceinline__
+#else
+#define NDZB_HD inline
+#endif
+
+namespace ndzb {
+
+constexpr int kCubeElems = 4096;       // reference src/ndzip/common.hh:368-381
+constexpr int kCubeThreads = 128;      // threads (= runs) per cube
+constexpr int kRunElems = 32;          // elements per run
+
+template<int Dims> struct side_of;     // reference src/ndzip/common.hh:371-378
+template<> struct side_of<1> { static constexpr int value = 4096; };
+template<> struct side_of<2> { static constexpr int value = 64; };
+template<> struct side_of<3> { static constexpr int value = 16; };
+
+template<typename Bits> struct codec_traits;
+template<> struct codec_traits<uint32_t> {
+    static constexpr int bits = 32;
+    static constexpr int chunks = 128;               // chunks per cube (cuda_codec.inl:190-194)
+    static constexpr int words32_per_elem = 1;
+    static constexpr int cube_words32 = 4096;        // input tile, 32-bit words
+    static constexpr int stage_words32 = 4096;       // plane staging tile (swizzled 128-byte rows)
+    static constexpr int max_cube_words = 4224;      // compressed bound in Bits words (common.hh:391-392)
+};
+template<> struct codec_traits<uint64_t> {
+    static constexpr int bits = 64;
+    static constexpr int chunks = 64;
+    static constexpr int words32_per_elem = 2;
+    static constexpr int cube_words32 = 8192;
+    static constexpr int stage_row_words32 = 130;    // padded row: [plane][chunk*2 + half], +2 pad words
+    static constexpr int stage_words32 = 64 * 130;
+    static constexpr int max_cube_words = 4160;
+};
+
+// ------------------------------------------------------------------------------------------------
+// bit helpers
+
+NDZB_HD uint32_t rotl1(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(v, v, 1);
+#else
+    return (v << 1) | (v >> 31);
+#endif
+}
+NDZB_HD uint64_t rotl1(uint64_t v) { return (v << 1) | (v >> 63); }
+NDZB_HD uint32_t rotr1(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(v, v, 1);
+#else
+    return (v >> 1) | (v << 31);
+#endif
+}
+NDZB_HD uint64_t rotr1(uint64_t v) { return (v >> 1) | (v << 63); }
+
+// reference src/ndzip/common.hh:446-449 — branch-free: xor with (sign ? 0x7f..f : 0)
+NDZB_HD uint32_t complement_negative(uint32_t v) {
+    return v ^ (static_cast<uint32_t>(static_cast<int32_t>(v) >> 31) & 0x7fffffffu);
+}
+NDZB_HD uint64_t complement_negative(uint64_t v) {
+    return v ^ (static_cast<uint64_t>(static_cast<int64_t>(v) >> 63) & 0x7fffffffffffffffull);
+}
+
+NDZB_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
+NDZB_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, y, sel);
+#else
+    const uint64_t xy = (static_cast<uint64_t>(y) << 32) | x;
+    uint32_t r = 0;
+    for (int n = 0; n < 4; ++n) r |= static_cast<uint32_t>((xy >> (8 * ((sel >> (4 * n)) & 7))) & 0xff) << (8 * n);
+    return r;
+#endif
+}
+
+// In-register 32x32 bit-matrix transpose, LSB-indexed: afterwards bit b of a[k] is what bit k of
+// a[b] was. Five butterfly stages; the 16- and 8-bit stages are byte permutes (1 PRMT per word),
+// the 4/2/1-bit stages are shift + bit-select (2 ops per word). 256 ALU ops per 1024 bits, versus
+// 32 ballots + 32 predicate set-ups PER CHUNK for a ballot transpose.
+NDZB_HD void transpose32(uint32_t *a) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t x = a[k], y = a[k + 16];
+        a[k] = byte_perm(x, y, 0x5410);        // low halves
+        a[k + 16] = byte_perm(x, y, 0x7632);   // high halves
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        if (k & 8) continue;
+        const uint32_t x = a[k], y = a[k + 8];
+        a[k] = byte_perm(x, y, 0x6240);        // even bytes
+        a[k + 8] = byte_perm(x, y, 0x7351);    // odd bytes
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        if (k & 4) continue;
+        const uint32_t x = a[k], y = a[k + 4];
+        a[k] = (x & 0x0f0f0f0fu) | ((y << 4) & 0xf0f0f0f0u);
+        a[k + 4] = ((x >> 4) & 0x0f0f0f0fu) | (y & 0xf0f0f0f0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        if (k & 2) continue;
+        const uint32_t x = a[k], y = a[k + 2];
+        a[k] = (x & 0x33333333u) | ((y << 2) & 0xccccccccu);
+        a[k + 2] = ((x >> 2) & 0x33333333u) | (y & 0xccccccccu);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        if (k & 1) continue;
+        const uint32_t x = a[k], y = a[k + 1];
+        a[k] = (x & 0x55555555u) | ((y << 1) & 0xaaaaaaaau);
+        a[k + 1] = ((x >> 1) & 0x55555555u) | (y & 0xaaaaaaaau);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory tile layout
+//
+// A cube is kept in 128-byte rows whose eight 16-byte units are XOR-swizzled with (row & 7) — the
+// pattern CU_TENSOR_MAP_SWIZZLE_128B produces, so a TMA tensor load can deposit the tile directly.
+// Row u holds run u (float: the whole run; double: 16 values, the run's other 16 values sit in row
+// u of a second 16 KiB region). Thread u reading its run with eight LDS.128 is then conflict-free:
+// the eight lanes of a quarter-warp touch eight different units.
+
+// 32-bit word index of 16-byte unit `unit` of row `row`
+NDZB_HD int tile_unit(int row, int unit) { return (row << 5) | ((unit ^ (row & 7)) << 2); }
+
+// 32-bit word index (of the low word) of cube-local element e
+template<typename Bits> NDZB_HD int tile_elem(int e);
+template<> NDZB_HD int tile_elem<uint32_t>(int e) {
+    const int run = e >> 5, j = e & 31;
+    return tile_unit(run, j >> 2) + (j & 3);
+}
+template<> NDZB_HD int tile_elem<uint64_t>(int e) {
+    const int run = e >> 5, j = e & 31;
+    return ((j >> 4) << 12) + tile_unit(run, (j & 15) >> 1) + ((j & 1) << 1);
+}
+
+struct alignas(16) quad { uint32_t x, y, z, w; };
+
+NDZB_HD quad ld_quad(const uint32_t *p) { return *reinterpret_cast<const quad *>(p); }
+NDZB_HD void st_quad(uint32_t *p, quad q) { *reinterpret_cast<quad *>(p) = q; }
+
+// Half-run `half` (16 values) of run `run`, bit-cast and rotated left by one (the reference fuses
+// the same rotate into its load, cuda_codec.inl:51-55).
+NDZB_HD void load_half_rot(const uint32_t *tile, int run, int half, uint32_t *out) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const quad q = ld_quad(tile + tile_unit(run, half * 4 + k));
+        out[4 * k + 0] = rotl1(q.x);
+        out[4 * k + 1] = rotl1(q.y);
+        out[4 * k + 2] = rotl1(q.z);
+        out[4 * k + 3] = rotl1(q.w);
+    }
+}
+NDZB_HD void load_half_rot(const uint32_t *tile, int run, int half, uint64_t *out) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const quad q = ld_quad(tile + (half << 12) + tile_unit(run, k));
+        out[2 * k + 0] = rotl1((static_cast<uint64_t>(q.y) << 32) | q.x);
+        out[2 * k + 1] = rotl1((static_cast<uint64_t>(q.w) << 32) | q.z);
+    }
+}
+
+// Last element (31) of run `run`, rotated.
+NDZB_HD uint32_t load_last_rot(const uint32_t *tile, int run, uint32_t) {
+    return rotl1(tile[tile_unit(run, 7) + 3]);
+}
+NDZB_HD uint64_t load_last_rot(const uint32_t *tile, int run, uint64_t) {
+    const int w = (1 << 12) + tile_unit(run, 7) + 2;
+    return rotl1((static_cast<uint64_t>(tile[w + 1]) << 32) | tile[w]);
+}
+
+// a[0..16) -= b[0..16)
+template<typename Bits>
+NDZB_HD void sub16(Bits *a, const Bits *b) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] -= b[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: residuals of run u
+//
+// The integer Lorenzo transform of the reference (rotate, x[i] -= x[i-1] along every axis in
+// Z/2^k, complement negatives; src/ndzip/common.hh:469-501, GPU version cuda_codec.inl:68-126)
+// evaluated as a stencil on the read-only tile: the per-axis differences commute, so the residual
+// of an element only depends on the 2^dims corner values, with out-of-cube neighbours = 0.
+// r[j] is the residual of cube-local element 32u + j, complement already applied.
+
+template<typename Bits, int Dims>
+NDZB_HD void residual_run(const uint32_t *tile, int u, Bits *r) {
+    Bits *lo = r, *hi = r + 16;
+    load_half_rot(tile, u, 0, lo);
+    load_half_rot(tile, u, 1, hi);
+    Bits left = 0;  // value preceding r[0] along x after the higher-axis differences
+
+    if constexpr (Dims == 1) {
+        // run u = elements [32u, 32u+32) of the 4096-long line
+        if (u > 0) left = load_last_rot(tile, u - 1, Bits{});
+    } else if constexpr (Dims == 2) {
+        // 64 x 64: run u = row y = u>>1, columns [32g, 32g+32) with g = u&1; the row above is run u-2
+        const int y = u >> 1, g = u & 1;
+        if (g) left = load_last_rot(tile, u - 1, Bits{});
+        if (y > 0) {
+            Bits up[16];
+            load_half_rot(tile, u - 2, 0, up);
+            sub16(lo, up);
+            load_half_rot(tile, u - 2, 1, up);
+            sub16(hi, up);
+            if (g) left -= load_last_rot(tile, u - 3, Bits{});
+        }
+    } else {
+        // 16^3: run u = rows y = 2p, 2p+1 of plane z, with z = u>>3, p = u&7.
+        // Row y-1 of the first row is the second half of run u-1; plane z-1 is 8 runs back.
+        const int z = u >> 3, p = u & 7;
+        Bits above[16];  // row 2p-1 of plane z (after the z difference)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) above[i] = 0;
+        if (p > 0) load_half_rot(tile, u - 1, 1, above);
+        if (z > 0) {
+            Bits back[16];
+            load_half_rot(tile, u - 8, 0, back);
+            sub16(lo, back);
+            load_half_rot(tile, u - 8, 1, back);
+            sub16(hi, back);
+            if (p > 0) {
+                load_half_rot(tile, u - 9, 1, back);
+                sub16(above, back);
+            }
+        }
+        // y difference: row 2p+1 -= row 2p, then row 2p -= row 2p-1
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            hi[i] -= lo[i];
+            lo[i] -= above[i];
+        }
+    }
+
+    // x difference, back to front so every step still sees the undifferenced predecessor
+    if constexpr (Dims == 3) {
+#pragma unroll
+        for (int i = 15; i >= 1; --i) {
+            hi[i] -= hi[i - 1];
+            lo[i] -= lo[i - 1];
+        }
+    } else {
+#pragma unroll
+        for (int j = 31; j >= 1; --j) r[j] -= r[j - 1];
+        r[0] -= left;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = complement_negative(r[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: bit planes of a run
+//
+// Plane i of a chunk (i = 0 is the MSB plane) has value j of the chunk at bit B-1-j
+// (reference src/ndzip/cpu_codec.inl:355-363). transpose32 is LSB-indexed, so values and planes are
+// fed / read in reversed register order, which is free with static register names.
+
+// float: planes[i] = plane i of chunk u; returns head = OR of the 32 residuals
+NDZB_HD uint32_t planes_of_run(const uint32_t *r, uint32_t *planes) {
+    uint32_t head = 0;
+    uint32_t a[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        head |= r[j];
+        a[31 - j] = r[j];
+    }
+    transpose32(a);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) planes[i] = a[31 - i];
+    return head;
+}
+
+// double: this thread's 32-bit half of planes 0..31 (from the high words) and of planes 32..63 (from
+// the low words) of the chunk its run belongs to. The thread with the chunk's first 32 values owns
+// bits 63..32 of every plane word, its partner bits 31..0 (cuda_codec.inl:241-264 has the same split).
+// Returns the partial head (OR over this run's 32 values).
+NDZB_HD uint64_t planes_of_run(const uint64_t *r, uint32_t *planes_hi, uint32_t *planes_lo) {
+    uint64_t head = 0;
+    uint32_t a[32], b[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        head |= r[j];
+        a[31 - j] = static_cast<uint32_t>(r[j] >> 32);
+        b[31 - j] = static_cast<uint32_t>(r[j]);
+    }
+    transpose32(a);
+    transpose32(b);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        planes_hi[i] = a[31 - i];
+        planes_lo[i] = b[31 - i];
+    }
+    return head;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plane staging tile
+//
+// float : row c (128 bytes, swizzled like the input tile) = the 32 planes of chunk c.
+//         Writer: thread c, eight STS.128. Reader: warp lane i <-> plane i, conflict-free.
+// double: word index plane*130 + 2*chunk + half (half 0 = bits 31..0). The 130-word pitch makes both
+//         the per-thread writes (fixed plane, consecutive chunk/half across lanes) and the
+//         warp-per-chunk 64-bit reads (fixed chunk, lane <-> plane) conflict-free.
+
+NDZB_HD int stage_word_f32(int chunk, int plane) {
+    return tile_unit(chunk, plane >> 2) + (plane & 3);
+}
+NDZB_HD int stage_word_f64(int chunk, int plane) {  // low half; +1 = high half
+    return plane * 130 + 2 * chunk;
+}
+
+NDZB_HD void stage_planes(uint32_t *stage, int chunk, const uint32_t *planes) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        st_quad(stage + tile_unit(chunk, g), quad{planes[4 * g], planes[4 * g + 1], planes[4 * g + 2], planes[4 * g + 3]});
+    }
+}
+
+// `first` = this thread holds the chunk's first 32 values (run 2c) and therefore the high halves.
+NDZB_HD void stage_planes(uint32_t *stage, int chunk, bool first, const uint32_t *planes_hi,
+        const uint32_t *planes_lo) {
+    uint32_t *base = stage + 2 * chunk + (first ? 1 : 0);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        base[i * 130] = planes_hi[i];
+        base[(i + 32) * 130] = planes_lo[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: warp-per-chunk compaction of the staged planes into the stream
+//
+// Lane `lane` moves plane `lane` (double: planes lane and lane+32) of chunk c. Plane i is emitted
+// exactly when bit B-1-i of the chunk head is set (cpu_codec.inl:514-538); its slot inside the chunk
+// is the number of set head bits above it, so no scan is needed. `cube_out` points at the cube's
+// first stream word, `body` is the chunk's first-plane offset in words (C + exclusive plane count).
+
+NDZB_HD void emit_chunk(const uint32_t *stage, int c, int lane, uint32_t head, uint32_t body, uint32_t *cube_out) {
+    const uint32_t above = lane == 0 ? 0u : (head >> (32 - lane));  // head bits of planes 0..lane-1
+    if ((head >> (31 - lane)) & 1u) cube_out[body + popc32(above)] = stage[stage_word_f32(c, lane)];
+}
+
+NDZB_HD void emit_chunk(const uint32_t *stage, int c, int lane, uint64_t head, uint32_t body, uint64_t *cube_out) {
+    const uint32_t head_hi = static_cast<uint32_t>(head >> 32), head_lo = static_cast<uint32_t>(head);
+    const uint32_t above_hi = lane == 0 ? 0u : (head_hi >> (32 - lane));
+    const uint32_t above_lo = lane == 0 ? 0u : (head_lo >> (32 - lane));
+    if ((head_hi >> (31 - lane)) & 1u) {
+        const uint32_t *w = stage + stage_word_f64(c, lane);
+        cube_out[body + popc32(above_hi)] = (static_cast<uint64_t>(w[1]) << 32) | w[0];
+    }
+    if ((head_lo >> (31 - lane)) & 1u) {
+        const uint32_t *w = stage + stage_word_f64(c, lane + 32);
+        cube_out[body + popc32(head_hi) + popc32(above_lo)] = (static_cast<uint64_t>(w[1]) << 32) | w[0];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// inverse: warp-per-chunk expansion of the stream into the staging tile (absent planes = 0)
+
+NDZB_HD void expand_chunk(uint32_t *stage, int c, int lane, uint32_t head, uint32_t body, const uint32_t *cube_in) {
+    const uint32_t above = lane == 0 ? 0u : (head >> (32 - lane));
+    uint32_t v = 0;
+    if ((head >> (31 - lane)) & 1u) v = cube_in[body + popc32(above)];
+    stage[stage_word_f32(c, lane)] = v;
+}
+
+NDZB_HD void expand_chunk(uint32_t *stage, int c, int lane, uint64_t head, uint32_t body, const uint64_t *cube_in) {
+    const uint32_t head_hi = static_cast<uint32_t>(head >> 32), head_lo = static_cast<uint32_t>(head);
+    const uint32_t above_hi = lane == 0 ? 0u : (head_hi >> (32 - lane));
+    const uint32_t above_lo = lane == 0 ? 0u : (head_lo >> (32 - lane));
+    uint64_t a = 0, b = 0;
+    if ((head_hi >> (31 - lane)) & 1u) a = cube_in[body + popc32(above_hi)];
+    if ((head_lo >> (31 - lane)) & 1u) b = cube_in[body + popc32(head_hi) + popc32(above_lo)];
+    uint32_t *wa = stage + stage_word_f64(c, lane);
+    uint32_t *wb = stage + stage_word_f64(c, lane + 32);
+    wa[0] = static_cast<uint32_t>(a);
+    wa[1] = static_cast<uint32_t>(a >> 32);
+    wb[0] = static_cast<uint32_t>(b);
+    wb[1] = static_cast<uint32_t>(b >> 32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// inverse: residuals of run u from the staged planes (transpose is an involution,
+// reference src/test/codec_generic_test.cc:65-81), complement undone (common.hh:505-507)
+
+NDZB_HD void run_of_planes(const uint32_t *stage, int u, uint32_t *r) {
+    uint32_t a[32];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const quad q = ld_quad(stage + tile_unit(u, g));
+        a[31 - (4 * g + 0)] = q.x;
+        a[31 - (4 * g + 1)] = q.y;
+        a[31 - (4 * g + 2)] = q.z;
+        a[31 - (4 * g + 3)] = q.w;
+    }
+    transpose32(a);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = complement_negative(a[31 - j]);
+}
+
+NDZB_HD void run_of_planes(const uint32_t *stage, int u, uint64_t *r) {
+    const int chunk = u >> 1;
+    const uint32_t *base = stage + 2 * chunk + ((u & 1) ? 0 : 1);
+    uint32_t a[32], b[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        a[31 - i] = base[i * 130];
+        b[31 - i] = base[(i + 32) * 130];
+    }
+    transpose32(a);
+    transpose32(b);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        r[j] = complement_negative((static_cast<uint64_t>(a[31 - j]) << 32) | b[31 - j]);
+    }
+}
+
+// Write run u back into the (swizzled) cube tile, e.g. after the in-register part of the inverse
+// transform. No rotate: the tile keeps transform-domain values until the final store.
+NDZB_HD void store_run(uint32_t *tile, int u, const uint32_t *r) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        st_quad(tile + tile_unit(u, g), quad{r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]});
+    }
+}
+NDZB_HD void store_run(uint32_t *tile, int u, const uint64_t *r) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t v0 = r[16 * h + 2 * k], v1 = r[16 * h + 2 * k + 1];
+            st_quad(tile + (h << 12) + tile_unit(u, k),
+                    quad{static_cast<uint32_t>(v0), static_cast<uint32_t>(v0 >> 32), static_cast<uint32_t>(v1),
+                            static_cast<uint32_t>(v1 >> 32)});
+        }
+    }
+}
+
+template<typename Bits> NDZB_HD Bits tile_load(const uint32_t *tile, int e);
+template<> NDZB_HD uint32_t tile_load<uint32_t>(const uint32_t *tile, int e) { return tile[tile_elem<uint32_t>(e)]; }
+template<> NDZB_HD uint64_t tile_load<uint64_t>(const uint32_t *tile, int e) {
+    const int w = tile_elem<uint64_t>(e);
+    return (static_cast<uint64_t>(tile[w + 1]) << 32) | tile[w];
+}
+template<typename Bits> NDZB_HD void tile_store(uint32_t *tile, int e, Bits v);
+template<> NDZB_HD void tile_store<uint32_t>(uint32_t *tile, int e, uint32_t v) { tile[tile_elem<uint32_t>(e)] = v; }
+template<> NDZB_HD void tile_store<uint64_t>(uint32_t *tile, int e, uint64_t v) {
+    const int w = tile_elem<uint64_t>(e);
+    tile[w] = static_cast<uint32_t>(v);
+    tile[w + 1] = static_cast<uint32_t>(v >> 32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry shared by kernels and host code
+
+struct grid_geom {
+    // element extents, slowest first, padded with 1 in front so index 2 is always the fastest
+    uint32_t n[3];
+    uint32_t cubes[3];       // whole cubes per dimension (padded with 1)
+    uint32_t num_cubes;
+};
+
+// Linear element offset of the first element of hypercube `hc` (row-major cube order, slowest
+// dimension first; reference src/ndzip/common.hh:414-433, 570-579).
+template<int Dims>
+NDZB_HD uint64_t cube_origin(const grid_geom &g, uint32_t hc) {
+    constexpr uint32_t side = side_of<Dims>::value;
+    if constexpr (Dims == 1) {
+        return static_cast<uint64_t>(hc) * side;
+    } else if constexpr (Dims == 2) {
+        const uint32_t cy = hc / g.cubes[2], cx = hc % g.cubes[2];
+        return (static_cast<uint64_t>(cy) * side) * g.n[2] + static_cast<uint64_t>(cx) * side;
+    } else {
+        const uint32_t cx = hc % g.cubes[2];
+        const uint32_t t = hc / g.cubes[2];
+        const uint32_t cy = t % g.cubes[1], cz = t / g.cubes[1];
+        return ((static_cast<uint64_t>(cz) * side) * g.n[1] + static_cast<uint64_t>(cy) * side) * g.n[2]
+                + static_cast<uint64_t>(cx) * side;
+    }
+}
+
+// Linear element offset, relative to the cube origin, of cube-local element e
+// (reference src/ndzip/gpu_common.hh:22-32).
+template<int Dims>
+NDZB_HD uint64_t cube_local_offset(const grid_geom &g, int e) {
+    if constexpr (Dims == 1) {
+        return static_cast<uint64_t>(e);
+    } else if constexpr (Dims == 2) {
+        return static_cast<uint64_t>(e >> 6) * g.n[2] + (e & 63);
+    } else {
+        return (static_cast<uint64_t>(e >> 8) * g.n[1] + ((e >> 4) & 15)) * g.n[2] + (e & 15);
+    }
+}
+
+// Border = elements outside every whole cube, in ascending linear index
+// (reference src/ndzip/common.hh:245-306, GPU counterpart gpu_common.hh:277-344).
+// Closed form for the i-th border element's linear index.
+struct border_geom {
+    uint64_t n1, n2;         // extents of the two fastest dimensions (1 if absent)
+    uint64_t in0, in1, in2;  // extents rounded down to whole cubes (slowest..fastest; 1-padded dims: n)
+    uint64_t slab_border;    // border elements per slowest-dimension index below in0: n1*n2 - in1*in2
+    uint64_t row_border;     // n2 - in2
+    uint64_t count;          // total border elements
+};
+
+NDZB_HD uint64_t border_linear_index(const border_geom &b, uint64_t i) {
+    const uint64_t head = b.in0 * b.slab_border;
+    if (i >= head) return b.in0 * b.n1 * b.n2 + (i - head);  // trailing slabs are border entirely
+    const uint64_t z = i / b.slab_border;
+    const uint64_t i2 = i % b.slab_border;
+    const uint64_t strip = b.in1 * b.row_border;  // x-tails of the rows that intersect cubes
+    uint64_t y, x;
+    if (i2 < strip) {
+        y = i2 / b.row_border;
+        x = b.in2 + i2 % b.row_border;
+    } else {
+        const uint64_t i3 = i2 - strip;
+        y = b.in1 + i3 / b.n2;
+        x = i3 % b.n2;
+    }
+    return (z * b.n1 + y) * b.n2 + x;
+}
+
+}  // namespace ndzb
