@@ -1,0 +1,74 @@
+"""ctypes binding of the C ABI in include/ndzip_b200.h. Fails loudly if the CUDA library is missing:
+there is no CPU fallback (BASELINE.json north_star)."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libndzip_b200.so")
+
+F32, F64 = 0, 1
+
+# every symbol include/ndzip_b200.h declares: (name, restype, argtypes)
+_vp, _u32, _u64, _i = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
+_pu32, _pu64 = ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint64)
+SYMBOLS = [
+    ("ndzb_ctx_create", _i, [ctypes.POINTER(_vp), _i, _i, _u32, _vp]),
+    ("ndzb_ctx_destroy", None, [_vp]),
+    ("ndzb_compress", _i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    ("ndzb_decompress", _i, [_vp, _vp, _vp, _i, _vp]),
+    ("ndzb_offload_compress", _i, [_vp, _vp, _i, _vp, _vp, _pu32, _pu64]),
+    ("ndzb_offload_decompress", _i, [_vp, _vp, _u32, _vp, _i, _vp, _pu32, _pu64]),
+    ("ndzb_compress_cubes", _i, [_vp, _vp, _i, _vp, _u32, _u32, _vp, _vp, _vp]),
+    ("ndzb_add_offset", _i, [_vp, _vp, _u32, _vp]),
+    ("ndzb_pack_border", _i, [_vp, _vp, _i, _vp, _vp]),
+    ("ndzb_decompress_cubes", _i, [_vp, _vp, _vp, _i, _vp, _u32, _u32]),
+    ("ndzb_num_hypercubes", _u32, [_i, _vp]),
+    ("ndzb_compressed_length_bound", _u64, [_i, _i, _vp]),
+    ("ndzb_border_element_count", _u64, [_i, _vp]),
+    ("ndzb_header_words", _u32, [_i, _u32]),
+    ("ndzb_compressed_cube_bound", _u32, [_i]),
+    ("ndzb_strerror", ctypes.c_char_p, [_i]),
+    ("ndzb_last_cuda_error", ctypes.c_char_p, []),
+    ("ndzb_version", ctypes.c_char_p, []),
+    ("ndzb_last_launch_count", _u32, [_vp]),
+]
+
+_lib = None
+
+
+class NdzipB200Error(RuntimeError):
+    """Mirrors the reference's std::runtime_error (src/ndzip/cuda_bits.cuh:165-169, cuda_codec.inl:557-559)."""
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NdzipB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m ndzip_b200.build` "
+                "(or __graft_entry__.build()). ndzip_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        lib = load()
+        msg = lib.ndzb_strerror(status).decode()
+        if status == -4:
+            msg += ": " + lib.ndzb_last_cuda_error().decode()
+        raise NdzipB200Error(msg)
+
+
+def size3(shape):
+    dims = len(shape)
+    if not 1 <= dims <= 3:
+        raise NdzipB200Error("Invalid dimensionality")  # reference src/ndzip/common.hh:642
+    return dims, (ctypes.c_uint32 * 3)(*(list(int(s) for s in shape) + [0] * (3 - dims)))

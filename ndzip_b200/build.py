@@ -1,0 +1,55 @@
+"""Builds libndzip_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libndzip_b200.so")
+SOURCES = ["ndzb_kernels.cu", "ndzb_capi.cu", "ndzip_adapter.cu"]
+HEADERS = ["ndzb_cube.cuh", "ndzb_ptx.cuh", "ndzb_kernels.cuh"]
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found; cannot build libndzip_b200.so")
+    return nvcc
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS if os.path.exists(os.path.join(CSRC, f))]
+    deps += [os.path.join(os.path.dirname(HERE), "include", "ndzip_b200.h")]
+    inc = os.path.join(os.path.dirname(HERE), "include", "ndzip")
+    if os.path.isdir(inc):
+        deps += [os.path.join(inc, f) for f in os.listdir(inc)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library if missing or older than its sources. Returns the .so path."""
+    if not force and not _stale():
+        return LIB
+    srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(os.path.dirname(HERE), "include"), "-o", LIB, *srcs]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    # nvcc must use the system g++ (the CXX in this image's environment points at a wrapper without libgomp specs)
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    subprocess.run(cmd, check=True, env=env)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,465 @@
+// ndzb_capi.cu — the C ABI declared in include/ndzip_b200.h: context, host-side stream arithmetic,
+// launch sequencing (what cuda_compressor_impl::compress / cuda_decompressor_impl::decompress /
+// cuda_offloader do in the reference, src/ndzip/cuda_codec.inl:554-761).
+#include "../../include/ndzip_b200.h"
+#include "ndzb_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+using namespace ndzb;
+
+namespace {
+
+thread_local char g_cuda_error[256] = "no error";
+
+int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_cuda_error, sizeof g_cuda_error, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return NDZB_ERR_CUDA;
+}
+int driver_fail(CUresult r, const char *what) {
+    snprintf(g_cuda_error, sizeof g_cuda_error, "%s: CUresult %d", what, static_cast<int>(r));
+    return NDZB_ERR_CUDA;
+}
+#define NDZB_CUDA(call)                                          \
+    do {                                                         \
+        const cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
+    } while (0)
+
+constexpr uint32_t side_for(int dims) { return dims == 1 ? 4096u : dims == 2 ? 64u : 16u; }
+
+bool valid_profile(int dtype, int dims) { return (dtype == NDZB_F32 || dtype == NDZB_F64) && dims >= 1 && dims <= 3; }
+
+grid_geom make_geom(int dims, const uint32_t *size) {
+    grid_geom g{};
+    const uint32_t side = side_for(dims);
+    for (int d = 0; d < 3; ++d) {
+        g.n[d] = 1;
+        g.cubes[d] = 1;
+    }
+    g.num_cubes = 1;
+    for (int d = 0; d < dims; ++d) {
+        g.n[3 - dims + d] = size[d];
+        g.cubes[3 - dims + d] = size[d] / side;
+        g.num_cubes *= size[d] / side;  // reference src/ndzip/common.hh:395-402
+    }
+    return g;
+}
+
+border_geom make_border(int dims, const uint32_t *size) {
+    const uint32_t side = side_for(dims);
+    uint64_t n[3] = {1, 1, 1}, in[3] = {1, 1, 1};
+    for (int d = 0; d < dims; ++d) {
+        n[3 - dims + d] = size[d];
+        in[3 - dims + d] = static_cast<uint64_t>(size[d] / side) * side;
+    }
+    border_geom b{};
+    b.n1 = n[1];
+    b.n2 = n[2];
+    b.in0 = in[0];
+    b.in1 = in[1];
+    b.in2 = in[2];
+    b.slab_border = n[1] * n[2] - in[1] * in[2];
+    b.row_border = n[2] - in[2];
+    b.count = n[0] * n[1] * n[2] - in[0] * in[1] * in[2];  // reference src/ndzip/common.hh:308-317
+    return b;
+}
+
+uint64_t num_elements(int dims, const uint32_t *size) {
+    uint64_t n = 1;
+    for (int d = 0; d < dims; ++d) n *= size[d];
+    return n;
+}
+
+uint32_t header_words(int dtype, uint32_t num_cubes) {
+    return dtype == NDZB_F32 ? num_cubes : (num_cubes + 1) / 2;  // reference src/ndzip/common.hh:350-352
+}
+
+size_t word_bytes(int dtype) { return dtype == NDZB_F32 ? 4 : 8; }
+
+std::mutex g_config_mutex;
+kernel_config g_config;
+bool g_configured = false;
+
+}  // namespace
+
+struct ndzb_ctx {
+    int dtype = 0;
+    int dims = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t desc_capacity = 0;
+    uint64_t *d_desc = nullptr;       // look-back descriptors
+    uint32_t *d_counters = nullptr;   // [0] ticket counter, [1] total compressed words of the last launch
+    uint32_t ticket_base = 0;
+    uint32_t epoch = 1;
+    int forced_path = -1;             // NDZB_LOAD_PATH=tma|vec16|scalar (profiling / tests)
+    uint32_t last_launches = 0;
+    // host-pointer ("offloader") staging, grown on demand and kept across calls
+    void *d_in = nullptr;
+    size_t d_in_bytes = 0;
+    void *d_out = nullptr;
+    size_t d_out_bytes = 0;
+    uint32_t *d_length = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+};
+
+namespace {
+
+int ensure_descriptors(ndzb_ctx *ctx, uint32_t cubes) {
+    if (cubes <= ctx->desc_capacity) return NDZB_OK;
+    // Growing synchronises the device (cudaFree/cudaMalloc); contexts sized by
+    // compressor_requirements never get here.
+    if (ctx->d_desc) NDZB_CUDA(cudaFree(ctx->d_desc));
+    ctx->d_desc = nullptr;
+    ctx->desc_capacity = 0;
+    NDZB_CUDA(cudaMalloc(&ctx->d_desc, static_cast<size_t>(cubes) * sizeof(uint64_t)));
+    NDZB_CUDA(cudaMemsetAsync(ctx->d_desc, 0, static_cast<size_t>(cubes) * sizeof(uint64_t), ctx->stream));
+    ctx->desc_capacity = cubes;
+    return NDZB_OK;
+}
+
+int ensure_buffer(void **buf, size_t *have, size_t want) {
+    if (want <= *have) return NDZB_OK;
+    if (*buf) NDZB_CUDA(cudaFree(*buf));
+    *buf = nullptr;
+    *have = 0;
+    NDZB_CUDA(cudaMalloc(buf, want));
+    *have = want;
+    return NDZB_OK;
+}
+
+load_path choose_path(const ndzb_ctx *ctx, const void *data, const grid_geom &g) {
+    const bool aligned = tma_compatible(ctx->dtype, ctx->dims, data, g);
+    if (ctx->forced_path == static_cast<int>(load_path::scalar)) return load_path::scalar;
+    if (!aligned) return load_path::scalar;
+    if (ctx->forced_path == static_cast<int>(load_path::vec16)) return load_path::vec16;
+    return load_path::tma;
+}
+
+// Enqueue the compression of cubes [hc_begin, hc_begin + count) (count > 0).
+int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g, uint32_t hc_begin, uint32_t count,
+        void *out_cubes, uint32_t *out_offsets, uint32_t *pad_word, uint32_t *length_out, uint32_t length_add) {
+    if (int rc = ensure_descriptors(ctx, count)) return rc;
+    const load_path path = choose_path(ctx, d_data, g);
+    CUtensorMap map{};
+    if (path == load_path::tma) {
+        const CUresult r = make_input_tensor_map(&map, ctx->dtype, ctx->dims, d_data, g);
+        if (r != CUDA_SUCCESS) return driver_fail(r, "cuTensorMapEncodeTiled");
+    }
+    const int per_sm = g_config.ctas_per_sm[ctx->dtype][ctx->dims - 1][static_cast<int>(path)];
+    const uint64_t resident = static_cast<uint64_t>(per_sm > 0 ? per_sm : 1) * g_config.num_sms;
+    const uint32_t grid = static_cast<uint32_t>(count < resident ? count : resident);
+
+    compress_launch a{};
+    a.data = d_data;
+    a.geom = g;
+    a.hc_begin = hc_begin;
+    a.count = count;
+    a.out_cubes = out_cubes;
+    a.out_offsets = out_offsets;
+    a.pad_word = pad_word;
+    a.total_words = ctx->d_counters + 1;
+    a.length_out = length_out;
+    a.length_add = length_add;
+    a.desc = ctx->d_desc;
+    a.ticket = ctx->d_counters;
+    a.ticket_base = ctx->ticket_base;
+    a.epoch = ctx->epoch;
+    const cudaError_t e = launch_compress(ctx->dtype, ctx->dims, path, a, &map, grid, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "compress_kernel launch");
+    ctx->last_launches += 1;
+    ctx->ticket_base += count + compress_ticket_overdraw(grid);  // wraps together with the device counter
+    if (++ctx->epoch >= (1u << 30)) {
+        NDZB_CUDA(cudaMemsetAsync(ctx->d_desc, 0, static_cast<size_t>(ctx->desc_capacity) * sizeof(uint64_t), ctx->stream));
+        ctx->epoch = 1;
+    }
+    return NDZB_OK;
+}
+
+bool store_vectorisable(const ndzb_ctx *ctx, const void *data, const grid_geom &g) {
+    return ctx->forced_path != static_cast<int>(load_path::scalar) && tma_compatible(ctx->dtype, ctx->dims, data, g);
+}
+
+int enqueue_decompress_range(ndzb_ctx *ctx, const void *stream_cubes, const uint32_t *offsets, void *d_data,
+        const grid_geom &g, uint32_t hc_begin, uint32_t count) {
+    const bool vec = store_vectorisable(ctx, d_data, g);
+    const int per_sm = g_config.dec_ctas_per_sm[ctx->dtype][ctx->dims - 1][vec ? 1 : 0];
+    const uint64_t resident = static_cast<uint64_t>(per_sm > 0 ? per_sm : 1) * g_config.num_sms;
+    const uint32_t grid = static_cast<uint32_t>(count < resident ? count : resident);
+    decompress_launch a{};
+    a.stream_cubes = stream_cubes;
+    a.offsets = offsets;
+    a.data = d_data;
+    a.geom = g;
+    a.hc_begin = hc_begin;
+    a.count = count;
+    const cudaError_t e = launch_decompress(ctx->dtype, ctx->dims, vec, a, grid, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "decompress_kernel launch");
+    ctx->last_launches += 1;
+    return NDZB_OK;
+}
+
+int check_call(const ndzb_ctx *ctx, int dims, const uint32_t *size) {
+    if (!ctx || !size) return NDZB_ERR_INVALID_ARGUMENT;
+    if (dims != ctx->dims) return NDZB_ERR_DIMS_MISMATCH;
+    if (num_elements(dims, size) >= (1ull << 32)) return NDZB_ERR_INVALID_ARGUMENT;  // reference index_type is uint32
+    return NDZB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ndzb_ctx_create(ndzb_ctx **out_ctx, int dtype, int dims, uint32_t max_hypercubes, void *cuda_stream) {
+    if (!out_ctx || !valid_profile(dtype, dims)) return NDZB_ERR_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_config_mutex);
+        if (!g_configured) {
+            const cudaError_t e = configure_kernels(g_config);
+            if (e != cudaSuccess) return cuda_fail(e, "configure_kernels (is a CUDA device present?)");
+            g_configured = true;
+        }
+    }
+    ndzb_ctx *ctx = new (std::nothrow) ndzb_ctx;
+    if (!ctx) return NDZB_ERR_ALLOC;
+    ctx->dtype = dtype;
+    ctx->dims = dims;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    if (const char *p = getenv("NDZB_LOAD_PATH")) {
+        if (!strcmp(p, "tma")) ctx->forced_path = 0;
+        else if (!strcmp(p, "vec16")) ctx->forced_path = 1;
+        else if (!strcmp(p, "scalar")) ctx->forced_path = 2;
+    }
+    auto fail = [&](int rc) {
+        ndzb_ctx_destroy(ctx);
+        return rc;
+    };
+    cudaError_t e = cudaMalloc(&ctx->d_counters, 2 * sizeof(uint32_t));
+    if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc counters"));
+    e = cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint32_t), ctx->stream);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMemsetAsync counters"));
+    if (max_hypercubes) {
+        if (int rc = ensure_descriptors(ctx, max_hypercubes)) return fail(rc);
+    }
+    e = cudaEventCreate(&ctx->ev_begin);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_end);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
+    *out_ctx = ctx;
+    return NDZB_OK;
+}
+
+void ndzb_ctx_destroy(ndzb_ctx *ctx) {
+    if (!ctx) return;
+    if (ctx->d_desc) cudaFree(ctx->d_desc);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_in) cudaFree(ctx->d_in);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->d_length) cudaFree(ctx->d_length);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    delete ctx;
+}
+
+int ndzb_compress(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t *size, void *d_stream,
+        uint32_t *d_length_words) {
+    if (int rc = check_call(ctx, dims, size)) return rc;
+    ctx->last_launches = 0;
+    const grid_geom g = make_geom(dims, size);
+    const border_geom bg = make_border(dims, size);
+    const uint32_t H = g.num_cubes;
+    const uint32_t hdr = header_words(ctx->dtype, H);
+    if (ndzb_compressed_length_bound(ctx->dtype, dims, size) >= (1ull << 32)) return NDZB_ERR_INVALID_ARGUMENT;
+    if ((H || bg.count) && (!d_data || !d_stream)) return NDZB_ERR_INVALID_ARGUMENT;
+
+    if (H > 0) {
+        uint32_t *offsets = static_cast<uint32_t *>(d_stream);
+        uint32_t *pad = (ctx->dtype == NDZB_F64 && (H & 1u)) ? offsets + H : nullptr;
+        void *cubes = static_cast<char *>(d_stream) + static_cast<size_t>(hdr) * word_bytes(ctx->dtype);
+        if (int rc = enqueue_compress_range(ctx, d_data, g, 0, H, cubes, offsets, pad, d_length_words,
+                    hdr + static_cast<uint32_t>(bg.count))) {
+            return rc;
+        }
+    }
+    if (bg.count > 0) {
+        const cudaError_t e = launch_pack_border(ctx->dtype, d_data, bg, d_stream, hdr, H ? ctx->d_counters + 1 : nullptr, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "pack_border launch");
+        ctx->last_launches += 1;
+    }
+    if (H == 0 && d_length_words) {
+        const cudaError_t e = launch_store_length(d_length_words, hdr + static_cast<uint32_t>(bg.count), nullptr, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "store_length launch");
+        ctx->last_launches += 1;
+    }
+    return NDZB_OK;
+}
+
+int ndzb_decompress(ndzb_ctx *ctx, const void *d_stream, void *d_data, int dims, const uint32_t *size) {
+    if (int rc = check_call(ctx, dims, size)) return rc;
+    ctx->last_launches = 0;
+    const grid_geom g = make_geom(dims, size);
+    const border_geom bg = make_border(dims, size);
+    const uint32_t H = g.num_cubes;
+    const uint32_t hdr = header_words(ctx->dtype, H);
+    if ((H || bg.count) && (!d_data || !d_stream)) return NDZB_ERR_INVALID_ARGUMENT;
+    const uint32_t *offsets = static_cast<const uint32_t *>(d_stream);
+    if (H > 0) {
+        const void *cubes = static_cast<const char *>(d_stream) + static_cast<size_t>(hdr) * word_bytes(ctx->dtype);
+        if (int rc = enqueue_decompress_range(ctx, cubes, offsets, d_data, g, 0, H)) return rc;
+    }
+    if (bg.count > 0) {
+        const cudaError_t e = launch_unpack_border(ctx->dtype, d_stream, offsets, H, hdr, bg, d_data, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "unpack_border launch");
+        ctx->last_launches += 1;
+    }
+    return NDZB_OK;
+}
+
+int ndzb_compress_cubes(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t *size, uint32_t hc_begin,
+        uint32_t hc_end, void *d_cubes, uint32_t *d_offsets_after, uint32_t *d_local_words) {
+    if (int rc = check_call(ctx, dims, size)) return rc;
+    ctx->last_launches = 0;
+    const grid_geom g = make_geom(dims, size);
+    if (hc_begin > hc_end || hc_end > g.num_cubes || !d_local_words) return NDZB_ERR_INVALID_ARGUMENT;
+    if (hc_begin == hc_end) {
+        const cudaError_t e = launch_store_length(d_local_words, 0, nullptr, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "store_length launch");
+        ctx->last_launches += 1;
+        return NDZB_OK;
+    }
+    if (!d_data || !d_cubes || !d_offsets_after) return NDZB_ERR_INVALID_ARGUMENT;
+    return enqueue_compress_range(ctx, d_data, g, hc_begin, hc_end - hc_begin, d_cubes, d_offsets_after, nullptr, d_local_words, 0);
+}
+
+int ndzb_add_offset(ndzb_ctx *ctx, uint32_t *d_offsets, uint32_t count, const uint32_t *d_base_words) {
+    if (!ctx || (count && (!d_offsets || !d_base_words))) return NDZB_ERR_INVALID_ARGUMENT;
+    const cudaError_t e = launch_add_offset(d_offsets, count, d_base_words, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "add_offset launch");
+    return NDZB_OK;
+}
+
+int ndzb_pack_border(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t *size, void *d_out) {
+    if (int rc = check_call(ctx, dims, size)) return rc;
+    const border_geom bg = make_border(dims, size);
+    if (bg.count == 0) return NDZB_OK;
+    if (!d_data || !d_out) return NDZB_ERR_INVALID_ARGUMENT;
+    const cudaError_t e = launch_pack_border(ctx->dtype, d_data, bg, d_out, 0, nullptr, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "pack_border launch");
+    return NDZB_OK;
+}
+
+int ndzb_decompress_cubes(ndzb_ctx *ctx, const void *d_stream, void *d_data, int dims, const uint32_t *size,
+        uint32_t hc_begin, uint32_t hc_end) {
+    if (int rc = check_call(ctx, dims, size)) return rc;
+    ctx->last_launches = 0;
+    const grid_geom g = make_geom(dims, size);
+    if (hc_begin > hc_end || hc_end > g.num_cubes) return NDZB_ERR_INVALID_ARGUMENT;
+    if (hc_begin == hc_end) return NDZB_OK;
+    if (!d_data || !d_stream) return NDZB_ERR_INVALID_ARGUMENT;
+    const uint32_t hdr = header_words(ctx->dtype, g.num_cubes);
+    const void *cubes = static_cast<const char *>(d_stream) + static_cast<size_t>(hdr) * word_bytes(ctx->dtype);
+    return enqueue_decompress_range(ctx, cubes, static_cast<const uint32_t *>(d_stream), d_data, g, hc_begin, hc_end - hc_begin);
+}
+
+int ndzb_offload_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uint32_t *size, void *h_stream,
+        uint32_t *length_words, uint64_t *kernel_ns) {
+    if (int rc = check_call(ctx, dims, size)) return rc;
+    if (!length_words) return NDZB_ERR_INVALID_ARGUMENT;
+    const size_t wb = word_bytes(ctx->dtype);
+    const size_t in_bytes = num_elements(dims, size) * wb;                                        // 64-bit, cf. cuda_codec.inl:681
+    const size_t bound_bytes = ndzb_compressed_length_bound(ctx->dtype, dims, size) * wb;
+    if (in_bytes && (!h_data || !h_stream)) return NDZB_ERR_INVALID_ARGUMENT;
+    if (int rc = ensure_buffer(&ctx->d_in, &ctx->d_in_bytes, in_bytes ? in_bytes : 16)) return rc;
+    if (int rc = ensure_buffer(&ctx->d_out, &ctx->d_out_bytes, bound_bytes ? bound_bytes : 16)) return rc;
+    if (!ctx->d_length) NDZB_CUDA(cudaMalloc(&ctx->d_length, sizeof(uint32_t)));
+    if (in_bytes) NDZB_CUDA(cudaMemcpyAsync(ctx->d_in, h_data, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NDZB_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    if (int rc = ndzb_compress(ctx, ctx->d_in, dims, size, ctx->d_out, ctx->d_length)) return rc;
+    NDZB_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
+    uint32_t len = 0;
+    NDZB_CUDA(cudaMemcpyAsync(&len, ctx->d_length, sizeof len, cudaMemcpyDeviceToHost, ctx->stream));
+    NDZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (len) NDZB_CUDA(cudaMemcpyAsync(h_stream, ctx->d_out, static_cast<size_t>(len) * wb, cudaMemcpyDeviceToHost, ctx->stream));
+    NDZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (kernel_ns) {
+        float ms = 0;
+        NDZB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+        *kernel_ns = static_cast<uint64_t>(static_cast<double>(ms) * 1e6);
+    }
+    *length_words = len;
+    return NDZB_OK;
+}
+
+int ndzb_offload_decompress(ndzb_ctx *ctx, const void *h_stream, uint32_t length_words, void *h_data, int dims,
+        const uint32_t *size, uint32_t *consumed_words, uint64_t *kernel_ns) {
+    if (int rc = check_call(ctx, dims, size)) return rc;
+    const size_t wb = word_bytes(ctx->dtype);
+    const size_t out_bytes = num_elements(dims, size) * wb;
+    const size_t in_bytes = static_cast<size_t>(length_words) * wb;
+    if (out_bytes && (!h_data || !h_stream)) return NDZB_ERR_INVALID_ARGUMENT;
+    if (int rc = ensure_buffer(&ctx->d_out, &ctx->d_out_bytes, in_bytes ? in_bytes : 16)) return rc;
+    if (int rc = ensure_buffer(&ctx->d_in, &ctx->d_in_bytes, out_bytes ? out_bytes : 16)) return rc;
+    if (in_bytes) NDZB_CUDA(cudaMemcpyAsync(ctx->d_out, h_stream, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NDZB_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    if (int rc = ndzb_decompress(ctx, ctx->d_out, ctx->d_in, dims, size)) return rc;
+    NDZB_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
+    if (out_bytes) NDZB_CUDA(cudaMemcpyAsync(h_data, ctx->d_in, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    NDZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (kernel_ns) {
+        float ms = 0;
+        NDZB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+        *kernel_ns = static_cast<uint64_t>(static_cast<double>(ms) * 1e6);
+    }
+    if (consumed_words) {
+        // header + last offset + border (reference cuda_codec.inl:740-745); the header lives in host memory
+        const grid_geom g = make_geom(dims, size);
+        const uint32_t H = g.num_cubes;
+        const uint32_t last = H ? static_cast<const uint32_t *>(h_stream)[H - 1] : 0u;
+        *consumed_words = header_words(ctx->dtype, H) + last + static_cast<uint32_t>(make_border(dims, size).count);
+    }
+    return NDZB_OK;
+}
+
+uint32_t ndzb_num_hypercubes(int dims, const uint32_t *size) {
+    if (dims < 1 || dims > 3 || !size) return 0;
+    return make_geom(dims, size).num_cubes;
+}
+
+uint64_t ndzb_border_element_count(int dims, const uint32_t *size) {
+    if (dims < 1 || dims > 3 || !size) return 0;
+    return make_border(dims, size).count;
+}
+
+uint32_t ndzb_header_words(int dtype, uint32_t num_hypercubes) { return header_words(dtype, num_hypercubes); }
+
+uint32_t ndzb_compressed_cube_bound(int dtype) { return dtype == NDZB_F32 ? 4224u : 4160u; }
+
+uint64_t ndzb_compressed_length_bound(int dtype, int dims, const uint32_t *size) {
+    if (!valid_profile(dtype, dims) || !size) return 0;
+    const uint64_t H = make_geom(dims, size).num_cubes;
+    return header_words(dtype, static_cast<uint32_t>(H)) + H * ndzb_compressed_cube_bound(dtype) + make_border(dims, size).count;
+}
+
+const char *ndzb_strerror(int status) {
+    switch (status) {
+        case NDZB_OK: return "ok";
+        case NDZB_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case NDZB_ERR_DIMS_MISMATCH: return "data dimensionality does not match compressor dimensionality";
+        case NDZB_ERR_CAPACITY: return "more hypercubes than the context was created for";
+        case NDZB_ERR_CUDA: return "CUDA error";
+        case NDZB_ERR_ALLOC: return "out of memory";
+        default: return "unknown ndzb status";
+    }
+}
+
+const char *ndzb_last_cuda_error(void) { return g_cuda_error; }
+
+const char *ndzb_version(void) { return "ndzip_b200 0.1 sm_100a"; }
+
+uint32_t ndzb_last_launch_count(const ndzb_ctx *ctx) { return ctx ? ctx->last_launches : 0; }
+
+}  // extern "C"

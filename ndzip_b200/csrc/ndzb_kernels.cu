@@ -1,0 +1,700 @@
+// ndzb_kernels.cu — the sm_100a kernels of the ndzip hot path and their launchers.
+//
+// compress_kernel   replaces compress_block + hierarchical_inclusive_scan + compact_all_chunks +
+//                   store_stream_length of the reference (src/ndzip/cuda_codec.inl:401-457, 507-511,
+//                   src/ndzip/cuda_bits.cuh:266-333) with ONE persistent kernel:
+//                     ticket -> TMA tensor load of the cube into a swizzled smem tile (double
+//                     buffered, mbarrier) -> per-thread stencil residuals + in-register 32x32 bit
+//                     transpose -> decoupled look-back over per-cube lengths (single pass, no
+//                     scratch stream, no second pass) -> warp-per-chunk compaction straight into the
+//                     final stream position + header entry.
+// decompress_kernel replaces decompress_block (cuda_codec.inl:477-492).
+// border kernels    replace compact_border / expand_border (cuda_codec.inl:463-474, 495-504).
+#include "ndzb_kernels.cuh"
+#include "ndzb_ptx.cuh"
+
+#include <type_traits>
+
+namespace ndzb {
+namespace {
+
+constexpr uint32_t kFullMask = 0xffffffffu;
+constexpr int kSlots = 2;   // input tiles in flight per CTA (TMA double buffering)
+constexpr int kWarps = kCubeThreads / 32;
+
+template<typename Bits>
+struct smem_plan {
+    using tr = codec_traits<Bits>;
+    static constexpr int tile_words = tr::cube_words32 > tr::stage_words32 ? tr::cube_words32 : tr::stage_words32;
+    static constexpr int slot_bytes = (tile_words * 4 + 1023) / 1024 * 1024;  // SWIZZLE_128B tiles need 1024-byte alignment
+};
+
+template<typename Bits>
+struct compress_aux {
+    uint64_t mbar[kSlots];
+    uint32_t ticket[kSlots];
+    Bits heads[codec_traits<Bits>::chunks];
+    uint32_t body_of[codec_traits<Bits>::chunks];
+    uint32_t warp_total[kWarps];
+    uint32_t prefix;
+};
+
+template<typename Bits>
+struct decompress_aux {
+    Bits heads[codec_traits<Bits>::chunks];
+    uint32_t body_of[codec_traits<Bits>::chunks];
+    uint32_t warp_total[kWarps];
+    Bits warp_sum[kWarps];
+};
+
+template<typename Bits>
+constexpr size_t compress_smem_bytes() {
+    return static_cast<size_t>(kSlots) * smem_plan<Bits>::slot_bytes + sizeof(compress_aux<Bits>);
+}
+template<typename Bits>
+constexpr size_t decompress_smem_bytes() {
+    return static_cast<size_t>(smem_plan<Bits>::slot_bytes) + sizeof(decompress_aux<Bits>);
+}
+
+__device__ __forceinline__ uint32_t popc_bits(uint32_t v) { return __popc(v); }
+__device__ __forceinline__ uint32_t popc_bits(uint64_t v) { return __popcll(v); }
+
+__device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(kFullMask, v, d);
+        if (lane >= d) v += up;
+    }
+    return v;
+}
+template<typename Bits>
+__device__ __forceinline__ Bits warp_inclusive_sum_bits(Bits v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Bits up = __shfl_up_sync(kFullMask, v, d);
+        if (lane >= d) v += up;
+    }
+    return v;
+}
+
+// ---- decoupled look-back descriptors -------------------------------------------------------------
+// One 64-bit word per cube: [63:34] epoch, [33:32] status, [31:0] value (words). The epoch makes the
+// descriptors of earlier launches read as "invalid", so the array never needs to be cleared.
+constexpr uint32_t kStatusAggregate = 1;  // value = this cube's compressed length
+constexpr uint32_t kStatusPrefix = 2;     // value = inclusive offset after this cube
+
+__device__ __forceinline__ uint64_t pack_desc(uint32_t epoch, uint32_t status, uint32_t value) {
+    return (static_cast<uint64_t>((epoch << 2) | status) << 32) | value;
+}
+__device__ __forceinline__ uint32_t desc_status(uint64_t d, uint32_t epoch) {
+    const uint32_t hi = static_cast<uint32_t>(d >> 32);
+    return (hi >> 2) == epoch ? (hi & 3u) : 0u;
+}
+
+// Exclusive offset of cube t (> 0) = sum of the lengths of cubes 0..t-1. Executed by one full warp;
+// lane l inspects predecessor idx-l. `first` is lane's pre-loaded sample of desc[t-1-lane].
+__device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, uint32_t epoch, int lane, uint64_t first) {
+    uint32_t exclusive = 0;
+    int64_t idx = static_cast<int64_t>(t) - 1;
+    uint64_t d = first;
+    bool have_sample = true;
+    while (true) {
+        const int64_t mine = idx - lane;
+        uint32_t status;
+        while (true) {
+            if (!have_sample) d = mine >= 0 ? ptx::ld_relaxed_gpu(desc + mine) : pack_desc(epoch, kStatusPrefix, 0);
+            have_sample = false;
+            status = desc_status(d, epoch);
+            if (!__any_sync(kFullMask, status == 0)) break;
+            __nanosleep(32);
+        }
+        const uint32_t prefix_lanes = __ballot_sync(kFullMask, status == kStatusPrefix);
+        const int nearest = prefix_lanes ? __ffs(prefix_lanes) - 1 : 32;
+        exclusive += __reduce_add_sync(kFullMask, lane <= nearest ? static_cast<uint32_t>(d) : 0u);
+        if (prefix_lanes) return exclusive;
+        idx -= 32;
+    }
+}
+
+// ---- cube input ------------------------------------------------------------------------------------
+
+template<typename Bits, int Dims>
+__device__ __forceinline__ void issue_tma_load(
+        uint32_t *slot, uint64_t *bar, const CUtensorMap *map, const grid_geom &g, uint32_t hc) {
+    constexpr uint32_t bytes = codec_traits<Bits>::cube_words32 * 4;
+    ptx::mbar_arrive_expect_tx(bar, bytes);
+    if constexpr (sizeof(Bits) == 4) {
+        if constexpr (Dims == 1) {
+            ptx::tma_load_2d(slot, map, bar, 0, static_cast<int>(hc * 128));
+        } else if constexpr (Dims == 2) {
+            const uint32_t cy = hc / g.cubes[2], cx = hc % g.cubes[2];
+            ptx::tma_load_3d(slot, map, bar, 0, static_cast<int>(cx * 2), static_cast<int>(cy * 64));
+        } else {
+            const uint32_t cx = hc % g.cubes[2], t = hc / g.cubes[2];
+            const uint32_t cy = t % g.cubes[1], cz = t / g.cubes[1];
+            ptx::tma_load_3d(slot, map, bar, static_cast<int>(cx * 16), static_cast<int>(cy * 16), static_cast<int>(cz * 16));
+        }
+    } else {
+        // two 16 KiB regions: region h holds the h-th 16-value half of every run
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t *dst = slot + (h << 12);
+            if constexpr (Dims == 1) {
+                ptx::tma_load_3d(dst, map, bar, 0, h, static_cast<int>(hc * 128));
+            } else if constexpr (Dims == 2) {
+                const uint32_t cy = hc / g.cubes[2], cx = hc % g.cubes[2];
+                ptx::tma_load_4d(dst, map, bar, 0, h, static_cast<int>(cx * 2), static_cast<int>(cy * 64));
+            } else {
+                const uint32_t cx = hc % g.cubes[2], t = hc / g.cubes[2];
+                const uint32_t cy = t % g.cubes[1], cz = t / g.cubes[1];
+                ptx::tma_load_4d(dst, map, bar, static_cast<int>(cx * 16), h, static_cast<int>(cy * 8), static_cast<int>(cz * 16));
+            }
+        }
+    }
+}
+
+// Cooperative global -> tile copy for shapes TMA cannot take (and as an A/B path for profiling).
+template<typename Bits, int Dims, bool Vec16>
+__device__ __forceinline__ void load_cube_ldg(uint32_t *tile, const Bits *data, const grid_geom &g, uint32_t hc, int tid) {
+    const uint64_t origin = cube_origin<Dims>(g, hc);
+    if constexpr (Vec16) {
+        constexpr int elems_per_unit = 16 / sizeof(Bits);
+        constexpr int units = kCubeElems / elems_per_unit;
+#pragma unroll 8
+        for (int q = tid; q < units; q += kCubeThreads) {
+            const int e = q * elems_per_unit;
+            const uint4 v = ptx::ldg_stream_v4(data + origin + cube_local_offset<Dims>(g, e));
+            *reinterpret_cast<uint4 *>(tile + tile_elem<Bits>(e)) = v;
+        }
+    } else {
+#pragma unroll 8
+        for (int e = tid; e < kCubeElems; e += kCubeThreads) {
+            tile_store<Bits>(tile, e, data[origin + cube_local_offset<Dims>(g, e)]);
+        }
+    }
+}
+
+// =====================================================================================================
+// compress
+// =====================================================================================================
+
+template<typename Bits, int Dims, load_path Path>
+__global__ void __launch_bounds__(kCubeThreads)
+        compress_kernel(const compress_launch a, const __grid_constant__ CUtensorMap tmap) {
+    using tr = codec_traits<Bits>;
+    constexpr int slot_words = smem_plan<Bits>::slot_bytes / 4;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint32_t *slots = reinterpret_cast<uint32_t *>(smem_raw);
+    auto &aux = *reinterpret_cast<compress_aux<Bits> *>(smem_raw + kSlots * smem_plan<Bits>::slot_bytes);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Bits *data = static_cast<const Bits *>(a.data);
+    Bits *out_cubes = static_cast<Bits *>(a.out_cubes);
+
+    // Work is handed out by a free-running ticket counter: ticket order == cube order, which is what
+    // makes spinning on predecessors in the look-back deadlock-free (a predecessor's ticket was drawn
+    // earlier, hence by a resident CTA). Each CTA keeps kSlots tickets in flight.
+    if (tid == 0) {
+        if constexpr (Path == load_path::tma) {
+            ptx::tma_prefetch_desc(&tmap);
+            for (int s = 0; s < kSlots; ++s) ptx::mbar_init(&aux.mbar[s], 1);
+            ptx::fence_mbar_init();
+        }
+        for (int s = 0; s < kSlots; ++s) {
+            const uint32_t t = atomicAdd(a.ticket, 1u) - a.ticket_base;
+            aux.ticket[s] = t;
+            if constexpr (Path == load_path::tma) {
+                if (t < a.count) issue_tma_load<Bits, Dims>(slots + s * slot_words, &aux.mbar[s], &tmap, a.geom, a.hc_begin + t);
+            }
+        }
+    }
+    __syncthreads();
+
+    for (uint32_t iter = 0;; ++iter) {
+        const int s = iter % kSlots;
+        const uint32_t t = aux.ticket[s];  // cube index within the launch's range
+        if (t >= a.count) break;
+        uint32_t *tile = slots + s * slot_words;
+
+        // draw the ticket this slot will serve next; its latency hides behind the cube's work
+        uint32_t next_ticket = 0;
+        if (tid == 0) next_ticket = atomicAdd(a.ticket, 1u) - a.ticket_base;
+
+        if constexpr (Path == load_path::tma) {
+            ptx::mbar_wait(&aux.mbar[s], (iter / kSlots) & 1u);
+        } else {
+            load_cube_ldg<Bits, Dims, Path == load_path::vec16>(tile, data, a.geom, a.hc_begin + t, tid);
+            __syncthreads();
+        }
+
+        // ---- phase 1: residuals of run `tid`, chunk heads, plane counts -------------------------------
+        Bits r[32];
+        residual_run<Bits, Dims>(tile, tid, r);
+
+        Bits head = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) head |= r[j];
+        uint32_t count;
+        if constexpr (sizeof(Bits) == 4) {
+            aux.heads[tid] = head;
+            count = popc_bits(head);
+        } else {
+            head |= __shfl_xor_sync(kFullMask, head, 1);  // chunk = two adjacent runs
+            if ((tid & 1) == 0) aux.heads[tid >> 1] = head;
+            count = (tid & 1) == 0 ? popc_bits(head) : 0u;
+        }
+        const uint32_t inclusive = warp_inclusive_sum(count, lane);
+        if (lane == 31) aux.warp_total[warp] = inclusive;
+        __syncthreads();  // B1: every read of the input tile is done; heads and warp totals visible
+
+        uint32_t before = 0, cube_words = tr::chunks;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t wt = aux.warp_total[w];
+            cube_words += wt;
+            if (w < warp) before += wt;
+        }
+        if (sizeof(Bits) == 4 || (tid & 1) == 0) {
+            aux.body_of[sizeof(Bits) == 4 ? tid : tid >> 1] = tr::chunks + before + inclusive - count;
+        }
+
+        // ---- warp 0 publishes the cube length and starts looking back ----------------------------------
+        uint64_t sample = 0;
+        if (warp == 0) {
+            if (lane == 0) {
+                ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, t == 0 ? kStatusPrefix : kStatusAggregate, cube_words));
+            }
+            const int64_t mine = static_cast<int64_t>(t) - 1 - lane;
+            sample = mine >= 0 ? ptx::ld_relaxed_gpu(a.desc + mine) : pack_desc(a.epoch, kStatusPrefix, 0);
+        }
+
+        // ---- phase 2: bit planes -> staging tile (in place over the input tile) --------------------
+        if constexpr (sizeof(Bits) == 4) {
+            uint32_t planes[32];
+            planes_of_run(r, planes);
+            stage_planes(tile, tid, planes);
+        } else {
+            uint32_t planes_hi[32], planes_lo[32];
+            planes_of_run(r, planes_hi, planes_lo);
+            stage_planes(tile, tid >> 1, (tid & 1) == 0, planes_hi, planes_lo);
+        }
+
+        if (warp == 0) {
+            const uint32_t exclusive = t == 0 ? 0u : look_back(a.desc, t, a.epoch, lane, sample);
+            if (lane == 0) {
+                const uint32_t after = exclusive + cube_words;
+                if (t != 0) ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, kStatusPrefix, after));
+                aux.prefix = exclusive;
+                a.out_offsets[t] = after;  // "offset_after", reference src/ndzip/common.hh:342-347
+                if (t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452
+                if (t == a.count - 1) {
+                    *a.total_words = after;
+                    if (a.length_out) *a.length_out = a.length_add + after;  // cuda_codec.inl:507-511
+                }
+            }
+        }
+        __syncthreads();  // B2: staging tile, body offsets and the cube's stream offset are visible
+
+        // ---- phase 3: heads + non-zero planes -> final stream position -------------------------------
+        Bits *cube_out = out_cubes + aux.prefix;
+        if (tid < tr::chunks) cube_out[tid] = aux.heads[tid];
+#pragma unroll 4
+        for (int c = warp; c < tr::chunks; c += kWarps) {
+            emit_chunk(tile, c, lane, aux.heads[c], aux.body_of[c], cube_out);
+        }
+        __syncthreads();  // B3: the slot is free
+
+        if (tid == 0) {
+            aux.ticket[s] = next_ticket;
+            if constexpr (Path == load_path::tma) {
+                if (next_ticket < a.count) {
+                    ptx::fence_proxy_async_smem();
+                    issue_tma_load<Bits, Dims>(tile, &aux.mbar[s], &tmap, a.geom, a.hc_begin + next_ticket);
+                }
+            }
+        }
+    }
+}
+
+// =====================================================================================================
+// decompress
+// =====================================================================================================
+
+// inclusive prefix sum along one column of the tile: elements first + k*stride, k < N
+template<typename Bits, int N>
+__device__ __forceinline__ void column_prefix(uint32_t *tile, int first, int stride) {
+    constexpr int kBatch = 16;
+    Bits acc = 0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < N; k0 += kBatch) {
+        Bits v[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) v[k] = tile_load<Bits>(tile, first + (k0 + k) * stride);
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            acc += v[k];
+            tile_store<Bits>(tile, first + (k0 + k) * stride, acc);
+        }
+    }
+}
+
+template<typename Bits, int Dims, bool Vec16>
+__global__ void __launch_bounds__(kCubeThreads) decompress_kernel(const decompress_launch a) {
+    using tr = codec_traits<Bits>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint32_t *tile = reinterpret_cast<uint32_t *>(smem_raw);
+    auto &aux = *reinterpret_cast<decompress_aux<Bits> *>(smem_raw + smem_plan<Bits>::slot_bytes);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Bits *stream_cubes = static_cast<const Bits *>(a.stream_cubes);
+    Bits *data = static_cast<Bits *>(a.data);
+
+    for (uint32_t t = blockIdx.x; t < a.count; t += gridDim.x) {
+        const uint32_t hc = a.hc_begin + t;
+        const uint32_t begin = hc ? __ldg(a.offsets + hc - 1) : 0u;  // reference src/ndzip/common.hh:350-358
+        const Bits *cube_in = stream_cubes + begin;
+
+        // ---- heads -> where each chunk's planes start ---------------------------------------------
+        uint32_t count = 0;
+        if (tid < tr::chunks) {
+            const Bits head = cube_in[tid];
+            aux.heads[tid] = head;
+            count = popc_bits(head);
+        }
+        const uint32_t inclusive = warp_inclusive_sum(count, lane);
+        if (lane == 31) aux.warp_total[warp] = inclusive;
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            if (w < warp) before += aux.warp_total[w];
+        }
+        if (tid < tr::chunks) aux.body_of[tid] = tr::chunks + before + inclusive - count;
+        __syncthreads();
+
+        // ---- warp-per-chunk expansion: stream -> plane staging tile ------------------------------
+#pragma unroll 4
+        for (int c = warp; c < tr::chunks; c += kWarps) {
+            expand_chunk(tile, c, lane, aux.heads[c], aux.body_of[c], cube_in);
+        }
+        __syncthreads();
+
+        // ---- per-thread: planes -> residuals of run `tid`; x-direction prefix sums ------------------
+        Bits r[32];
+        run_of_planes(tile, tid, r);
+        if constexpr (Dims == 3) {
+#pragma unroll
+            for (int i = 1; i < 16; ++i) {
+                r[i] += r[i - 1];
+                r[16 + i] += r[16 + i - 1];
+            }
+        } else {
+#pragma unroll
+            for (int j = 1; j < 32; ++j) r[j] += r[j - 1];
+        }
+        if constexpr (Dims == 1) {
+            // exclusive block scan of the run totals
+            const Bits total = r[31];
+            const Bits incl = warp_inclusive_sum_bits<Bits>(total, lane);
+            if (lane == 31) aux.warp_sum[warp] = incl;
+            __syncthreads();
+            Bits carry = incl - total;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                if (w < warp) carry += aux.warp_sum[w];
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] += carry;
+        } else if constexpr (Dims == 2) {
+            // a row is two adjacent runs: the right half continues from the left half's total
+            const Bits left = __shfl_up_sync(kFullMask, r[31], 1);
+            if (tid & 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] += left;
+            }
+        }
+        // the double staging tile is not thread-private: everyone must have read before anyone writes
+        if constexpr (sizeof(Bits) == 8) __syncthreads();
+        store_run(tile, tid, r);
+        __syncthreads();
+
+        // ---- remaining axes: column prefix sums in shared memory -------------------------------------
+        if constexpr (Dims == 2) {
+            if (tid < 64) column_prefix<Bits, 64>(tile, tid, 64);
+            __syncthreads();
+        } else if constexpr (Dims == 3) {
+#pragma unroll
+            for (int q = tid; q < 256; q += kCubeThreads) column_prefix<Bits, 16>(tile, (q >> 4) * 256 + (q & 15), 16);
+            __syncthreads();
+#pragma unroll
+            for (int q = tid; q < 256; q += kCubeThreads) column_prefix<Bits, 16>(tile, q, 256);
+            __syncthreads();
+        }
+
+        // ---- rotate back and store (reference cuda_codec.inl:58-65) ----------------------------------
+        const uint64_t origin = cube_origin<Dims>(a.geom, hc);
+        if constexpr (Vec16) {
+            constexpr int elems_per_unit = 16 / sizeof(Bits);
+            constexpr int units = kCubeElems / elems_per_unit;
+#pragma unroll 8
+            for (int q = tid; q < units; q += kCubeThreads) {
+                const int e = q * elems_per_unit;
+                uint4 v = *reinterpret_cast<const uint4 *>(tile + tile_elem<Bits>(e));
+                if constexpr (sizeof(Bits) == 4) {
+                    v.x = rotr1(v.x); v.y = rotr1(v.y); v.z = rotr1(v.z); v.w = rotr1(v.w);
+                } else {
+                    const uint32_t x = v.x, z = v.z;
+                    v.x = __funnelshift_r(v.x, v.y, 1); v.y = __funnelshift_r(v.y, x, 1);
+                    v.z = __funnelshift_r(v.z, v.w, 1); v.w = __funnelshift_r(v.w, z, 1);
+                }
+                ptx::stg_stream_v4(data + origin + cube_local_offset<Dims>(a.geom, e), v);
+            }
+        } else {
+#pragma unroll 8
+            for (int e = tid; e < kCubeElems; e += kCubeThreads) {
+                data[origin + cube_local_offset<Dims>(a.geom, e)] = rotr1(tile_load<Bits>(tile, e));
+            }
+        }
+        __syncthreads();  // tile is reused by the next cube
+    }
+}
+
+// =====================================================================================================
+// border, small utilities
+// =====================================================================================================
+
+template<typename Bits>
+__global__ void pack_border_kernel(
+        const Bits *data, border_geom bg, Bits *stream_words, uint64_t border_base, const uint32_t *total_words) {
+    const uint64_t base = border_base + (total_words ? *total_words : 0u);
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < bg.count;
+            i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        stream_words[base + i] = data[border_linear_index(bg, i)];
+    }
+}
+
+template<typename Bits>
+__global__ void unpack_border_kernel(const Bits *stream_words, const uint32_t *offsets, uint32_t num_cubes,
+        uint64_t header_words, border_geom bg, Bits *data) {
+    const uint64_t base = header_words + (num_cubes ? offsets[num_cubes - 1] : 0u);  // common.hh:365
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < bg.count;
+            i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        data[border_linear_index(bg, i)] = stream_words[base + i];
+    }
+}
+
+__global__ void add_offset_kernel(uint32_t *offsets, uint32_t count, const uint32_t *base) {
+    const uint32_t b = *base;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) offsets[i] += b;
+}
+
+__global__ void store_length_kernel(uint32_t *length_out, uint32_t value, const uint32_t *plus) {
+    *length_out = value + (plus ? *plus : 0u);
+}
+
+// ---- kernel tables ----------------------------------------------------------------------------------
+
+using compress_fn = void (*)(const compress_launch, const CUtensorMap);
+using decompress_fn = void (*)(const decompress_launch);
+
+template<typename Bits, int Dims>
+compress_fn compress_for(load_path p) {
+    switch (p) {
+        case load_path::tma: return compress_kernel<Bits, Dims, load_path::tma>;
+        case load_path::vec16: return compress_kernel<Bits, Dims, load_path::vec16>;
+        default: return compress_kernel<Bits, Dims, load_path::scalar>;
+    }
+}
+compress_fn compress_entry(int dtype, int dims, load_path p) {
+    if (dtype == 0) {
+        return dims == 1 ? compress_for<uint32_t, 1>(p) : dims == 2 ? compress_for<uint32_t, 2>(p) : compress_for<uint32_t, 3>(p);
+    }
+    return dims == 1 ? compress_for<uint64_t, 1>(p) : dims == 2 ? compress_for<uint64_t, 2>(p) : compress_for<uint64_t, 3>(p);
+}
+template<typename Bits, int Dims>
+decompress_fn decompress_for(bool vec) {
+    return vec ? decompress_kernel<Bits, Dims, true> : decompress_kernel<Bits, Dims, false>;
+}
+decompress_fn decompress_entry(int dtype, int dims, bool vec) {
+    if (dtype == 0) {
+        return dims == 1 ? decompress_for<uint32_t, 1>(vec) : dims == 2 ? decompress_for<uint32_t, 2>(vec) : decompress_for<uint32_t, 3>(vec);
+    }
+    return dims == 1 ? decompress_for<uint64_t, 1>(vec) : dims == 2 ? decompress_for<uint64_t, 2>(vec) : decompress_for<uint64_t, 3>(vec);
+}
+
+size_t compress_smem(int dtype) { return dtype == 0 ? compress_smem_bytes<uint32_t>() : compress_smem_bytes<uint64_t>(); }
+size_t decompress_smem(int dtype) { return dtype == 0 ? decompress_smem_bytes<uint32_t>() : decompress_smem_bytes<uint64_t>(); }
+
+}  // namespace
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+
+uint32_t compress_ticket_overdraw(uint32_t grid) {
+    return grid * kSlots;  // every CTA draws kSlots tickets up front and one more per cube it processes
+}
+
+cudaError_t configure_kernels(kernel_config &cfg) {
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    err = cudaDeviceGetAttribute(&cfg.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (err != cudaSuccess) return err;
+    for (int dtype = 0; dtype < 2; ++dtype) {
+        for (int dims = 1; dims <= 3; ++dims) {
+            for (int p = 0; p < 3; ++p) {
+                auto fn = compress_entry(dtype, dims, static_cast<load_path>(p));
+                err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(compress_smem(dtype)));
+                if (err != cudaSuccess) return err;
+                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                        &cfg.ctas_per_sm[dtype][dims - 1][p], fn, kCubeThreads, compress_smem(dtype));
+                if (err != cudaSuccess) return err;
+            }
+            for (int v = 0; v < 2; ++v) {
+                auto fn = decompress_entry(dtype, dims, v != 0);
+                err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(decompress_smem(dtype)));
+                if (err != cudaSuccess) return err;
+                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                        &cfg.dec_ctas_per_sm[dtype][dims - 1][v], fn, kCubeThreads, decompress_smem(dtype));
+                if (err != cudaSuccess) return err;
+            }
+        }
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_compress(int dtype, int dims, load_path path, const compress_launch &args, const CUtensorMap *tmap,
+        uint32_t grid, cudaStream_t stream) {
+    static const CUtensorMap dummy{};
+    compress_entry(dtype, dims, path)<<<grid, kCubeThreads, compress_smem(dtype), stream>>>(args, tmap ? *tmap : dummy);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decompress(int dtype, int dims, bool vec_store, const decompress_launch &args, uint32_t grid,
+        cudaStream_t stream) {
+    decompress_entry(dtype, dims, vec_store)<<<grid, kCubeThreads, decompress_smem(dtype), stream>>>(args);
+    return cudaGetLastError();
+}
+
+static uint32_t border_grid(uint64_t count) {
+    const uint64_t blocks = (count + 255) / 256;
+    return static_cast<uint32_t>(blocks < 148u * 16u ? (blocks ? blocks : 1) : 148u * 16u);
+}
+
+cudaError_t launch_pack_border(int dtype, const void *data, const border_geom &bg, void *stream_words,
+        uint64_t border_base, const uint32_t *total_words, cudaStream_t stream) {
+    if (dtype == 0) {
+        pack_border_kernel<uint32_t><<<border_grid(bg.count), 256, 0, stream>>>(
+                static_cast<const uint32_t *>(data), bg, static_cast<uint32_t *>(stream_words), border_base, total_words);
+    } else {
+        pack_border_kernel<uint64_t><<<border_grid(bg.count), 256, 0, stream>>>(
+                static_cast<const uint64_t *>(data), bg, static_cast<uint64_t *>(stream_words), border_base, total_words);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_border(int dtype, const void *stream_words, const uint32_t *offsets, uint32_t num_cubes,
+        uint64_t header_words, const border_geom &bg, void *data, cudaStream_t stream) {
+    if (dtype == 0) {
+        unpack_border_kernel<uint32_t><<<border_grid(bg.count), 256, 0, stream>>>(
+                static_cast<const uint32_t *>(stream_words), offsets, num_cubes, header_words, bg, static_cast<uint32_t *>(data));
+    } else {
+        unpack_border_kernel<uint64_t><<<border_grid(bg.count), 256, 0, stream>>>(
+                static_cast<const uint64_t *>(stream_words), offsets, num_cubes, header_words, bg, static_cast<uint64_t *>(data));
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_add_offset(uint32_t *offsets, uint32_t count, const uint32_t *base, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    const uint32_t blocks = (count + 255) / 256;
+    add_offset_kernel<<<blocks < 1184u ? blocks : 1184u, 256, 0, stream>>>(offsets, count, base);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_store_length(uint32_t *length_out, uint32_t value, const uint32_t *plus, cudaStream_t stream) {
+    store_length_kernel<<<1, 1, 0, stream>>>(length_out, value, plus);
+    return cudaGetLastError();
+}
+
+// ---- TMA tensor maps --------------------------------------------------------------------------------
+
+bool tma_compatible(int dtype, int dims, const void *data, const grid_geom &g) {
+    if (reinterpret_cast<uintptr_t>(data) % 16 != 0 || g.num_cubes == 0) return false;
+    if (dims == 1) return true;                       // rows of 128 bytes at 128-byte pitch
+    const uint32_t nx = g.n[2];
+    return dtype == 0 ? nx % 4 == 0 : nx % 2 == 0;    // every global stride must be a multiple of 16 bytes
+}
+
+namespace {
+using encode_tiled_fn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_tiled_fn get_encode_tiled() {
+    static encode_tiled_fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess
+                || q != cudaDriverEntryPointSuccess) {
+            p = nullptr;
+        }
+        return reinterpret_cast<encode_tiled_fn>(p);
+    }();
+    return fn;
+}
+}  // namespace
+
+CUresult make_input_tensor_map(CUtensorMap *map, int dtype, int dims, const void *data, const grid_geom &g) {
+    const auto encode = get_encode_tiled();
+    if (!encode) return CUDA_ERROR_NOT_SUPPORTED;
+    const uint64_t n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];  // slowest .. fastest (1-padded in front)
+    cuuint64_t gdim[5] = {1, 1, 1, 1, 1};
+    cuuint64_t gstride[4] = {16, 16, 16, 16};  // bytes, for dimensions 1..rank-1
+    cuuint32_t box[5] = {1, 1, 1, 1, 1};
+    cuuint32_t estride[5] = {1, 1, 1, 1, 1};
+    cuuint32_t rank = 0;
+    CUtensorMapDataType type;
+    if (dtype == 0) {
+        type = CU_TENSOR_MAP_DATA_TYPE_UINT32;
+        if (dims == 1) {            // [rows of 32][32]
+            rank = 2;
+            gdim[0] = 32; gdim[1] = n2 / 32;
+            gstride[0] = 128;
+            box[0] = 32; box[1] = 128;
+        } else if (dims == 2) {     // [y][x / 32][32]
+            rank = 3;
+            gdim[0] = 32; gdim[1] = n2 / 32; gdim[2] = n1;
+            gstride[0] = 128; gstride[1] = n2 * 4;
+            box[0] = 32; box[1] = 2; box[2] = 64;
+        } else {                    // [z][y][x]
+            rank = 3;
+            gdim[0] = n2; gdim[1] = n1; gdim[2] = n0;
+            gstride[0] = n2 * 4; gstride[1] = n1 * n2 * 4;
+            box[0] = 16; box[1] = 16; box[2] = 16;
+        }
+    } else {
+        type = CU_TENSOR_MAP_DATA_TYPE_UINT64;
+        if (dims == 1) {            // [runs][half][16]
+            rank = 3;
+            gdim[0] = 16; gdim[1] = 2; gdim[2] = n2 / 32;
+            gstride[0] = 128; gstride[1] = 256;
+            box[0] = 16; box[1] = 1; box[2] = 128;
+        } else if (dims == 2) {     // [y][x / 32][half][16]
+            rank = 4;
+            gdim[0] = 16; gdim[1] = 2; gdim[2] = n2 / 32; gdim[3] = n1;
+            gstride[0] = 128; gstride[1] = 256; gstride[2] = n2 * 8;
+            box[0] = 16; box[1] = 1; box[2] = 2; box[3] = 64;
+        } else {                    // [z][y / 2][y parity][x]
+            rank = 4;
+            gdim[0] = n2; gdim[1] = 2; gdim[2] = n1 / 2; gdim[3] = n0;
+            gstride[0] = n2 * 8; gstride[1] = n2 * 16; gstride[2] = n1 * n2 * 8;
+            box[0] = 16; box[1] = 1; box[2] = 8; box[3] = 16;
+        }
+    }
+    return encode(map, type, rank, const_cast<void *>(data), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+}  // namespace ndzb

@@ -1,0 +1,77 @@
+// ndzb_kernels.cuh — launch interface between the C ABI (ndzb_capi.cu) and the kernels (ndzb_kernels.cu).
+#pragma once
+
+#include "ndzb_cube.cuh"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace ndzb {
+
+enum class load_path : int {
+    tma = 0,     // cp.async.bulk.tensor into the swizzled tile, double-buffered (needs 16-byte aligned base/strides)
+    vec16 = 1,   // 16-byte global loads + manual swizzle (same alignment requirement, no TMA)
+    scalar = 2,  // element-wise global loads: any shape / alignment
+};
+
+struct compress_launch {
+    const void *data;          // element 0 of the (global) array
+    grid_geom geom;
+    uint32_t hc_begin;         // first hypercube of the range this launch compresses
+    uint32_t count;            // number of hypercubes in the range (> 0)
+    void *out_cubes;           // bits_type*: where the range's first compressed cube goes
+    uint32_t *out_offsets;     // inclusive word offsets, entry i belongs to cube hc_begin + i
+    uint32_t *pad_word;        // nullable: header padding word to be zeroed (f64, odd H)
+    uint32_t *total_words;     // device scalar: compressed words of the whole range
+    uint32_t *length_out;      // nullable: receives length_add + total
+    uint32_t length_add;
+    uint64_t *desc;            // decoupled look-back descriptors, >= count entries
+    uint32_t *ticket;          // free-running ticket counter
+    uint32_t ticket_base;      // value of *ticket when this launch starts
+    uint32_t epoch;            // tag that invalidates descriptors of earlier launches (< 2^30)
+};
+
+struct decompress_launch {
+    const void *stream_cubes;      // bits_type*: first compressed cube of the stream (after the header)
+    const uint32_t *offsets;       // the stream header: inclusive offsets of ALL cubes
+    void *data;                    // element 0 of the (global) output array
+    grid_geom geom;
+    uint32_t hc_begin, count;
+};
+
+struct kernel_config {
+    int num_sms = 0;
+    int ctas_per_sm[2][3][3] = {};  // [dtype][dims-1][load_path] occupancy of the compress kernels
+    int dec_ctas_per_sm[2][3][2] = {};  // [dtype][dims-1][vectorised store?]
+};
+
+// Queries occupancy and opts the kernels into their dynamic shared memory size. Returns cudaError_t.
+cudaError_t configure_kernels(kernel_config &cfg);
+
+// Number of tickets a compress launch of `grid` CTAs draws beyond `count` (see ndzb_kernels.cu).
+uint32_t compress_ticket_overdraw(uint32_t grid);
+
+// All launchers are asynchronous on `stream` and return the launch error, if any.
+cudaError_t launch_compress(int dtype, int dims, load_path path, const compress_launch &args, const CUtensorMap *tmap,
+        uint32_t grid, cudaStream_t stream);
+cudaError_t launch_decompress(int dtype, int dims, bool vec_store, const decompress_launch &args, uint32_t grid,
+        cudaStream_t stream);
+
+// Border: stream_border[i] = bits(data[border_linear_index(i)]) and the inverse.
+// `total_words` (nullable) is a device scalar added to border_base (the compressed words, only known on device).
+cudaError_t launch_pack_border(int dtype, const void *data, const border_geom &bg, void *stream_words,
+        uint64_t border_base, const uint32_t *total_words, cudaStream_t stream);
+cudaError_t launch_unpack_border(int dtype, const void *stream_words, const uint32_t *offsets, uint32_t num_cubes,
+        uint64_t header_words, const border_geom &bg, void *data, cudaStream_t stream);
+
+// offsets[i] += *base for i < count; also used to store a constant length.
+cudaError_t launch_add_offset(uint32_t *offsets, uint32_t count, const uint32_t *base, cudaStream_t stream);
+cudaError_t launch_store_length(uint32_t *length_out, uint32_t value, const uint32_t *plus, cudaStream_t stream);
+
+// TMA tensor map for the compress input tile of (dtype, dims); returns false if the shape / pointer
+// does not meet TMA's alignment rules (caller then uses vec16 or scalar).
+bool tma_compatible(int dtype, int dims, const void *data, const grid_geom &g);
+// Fills `map`; returns CUDA_SUCCESS or the driver error.
+CUresult make_input_tensor_map(CUtensorMap *map, int dtype, int dims, const void *data, const grid_geom &g);
+
+}  // namespace ndzb

@@ -1,0 +1,222 @@
+"""Multi-GPU sharding of the hot path (new work, SURVEY.md §5 / §8e — the reference is single-GPU).
+
+Hypercubes are independent, so the grid is cut into slabs along the slowest dimension, one slab per
+rank (one process per GPU). Every rank compresses its slab into a self-contained local ndzip stream.
+The only data-path exchange is the cross-rank exclusive scan of the per-rank compressed word counts
+(one ``all_gather`` of a single integer per rank over NCCL/NVLink): it turns the local "offset_after"
+header entries into the global ones (reference src/ndzip/common.hh:342-358). The final stream gather
+(cube segments to one root over NVLink) is optional and timed separately: it is bounded by one GPU's
+NVLink ingest, far below the compression rate.
+
+Global stream of the whole grid == [fixed-up headers, rank order][cube segments, rank order]
+[border segments, rank order] — bit-identical to the single-GPU / CPU stream, because with slabs of
+whole cube rows both the cube order and the ascending-linear-index border order concatenate.
+
+The host-side logic here is backend-agnostic (``gloo`` on CPU in tests, ``nccl`` on GPUs).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+SIDE = {1: 4096, 2: 64, 3: 16}
+
+
+def slab_partition(shape: Sequence[int], world_size: int) -> List[Tuple[int, int]]:
+    """[begin, end) along dimension 0 for every rank. Interior boundaries are multiples of the cube
+    side; cube rows are dealt out as evenly as possible; the last rank also takes the trailing
+    partial rows (the border slab)."""
+    dims = len(shape)
+    side = SIDE[dims]
+    cube_rows = shape[0] // side
+    bounds = [0]
+    for r in range(world_size):
+        rows = cube_rows // world_size + (1 if r < cube_rows % world_size else 0)
+        bounds.append(bounds[-1] + rows * side)
+    bounds[-1] = shape[0]
+    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+
+
+def slab_shape(shape: Sequence[int], span: Tuple[int, int]) -> Tuple[int, ...]:
+    return (span[1] - span[0],) + tuple(shape[1:])
+
+
+def cubes_in(shape: Sequence[int]) -> int:
+    side = SIDE[len(shape)]
+    n = 1
+    for s in shape:
+        n *= s // side
+    return n
+
+
+def border_in(shape: Sequence[int]) -> int:
+    side = SIDE[len(shape)]
+    total, inner = 1, 1
+    for s in shape:
+        total *= s
+        inner *= s // side * side
+    return total - inner
+
+
+def header_words(dtype, num_cubes: int) -> int:
+    return num_cubes if np.dtype(dtype).itemsize == 4 else (num_cubes + 1) // 2
+
+
+@dataclass
+class ShardLayout:
+    """Where one rank's pieces live in its local stream and in the global stream (all in words)."""
+    rank: int
+    world_size: int
+    local_shape: Tuple[int, ...]
+    local_cubes: int
+    cube_index_base: int      # global hypercube index of the rank's first cube
+    local_header_words: int
+    local_cube_words: int     # compressed cube words of this rank
+    local_border: int
+    global_cubes: int
+    global_header_words: int
+    cube_word_base: int       # exclusive scan of local_cube_words over ranks
+    total_cube_words: int
+    border_base: int          # exclusive scan of local_border over ranks
+    total_border: int
+    global_shape: Tuple[int, ...] = ()
+    all_cube_words: Tuple[int, ...] = ()   # every rank's compressed cube words (the gathered vector)
+    dtype_itemsize: int = 4
+
+    def peer(self, r: int) -> "ShardLayout":
+        """Layout of rank r, derived from the same gathered counts (no further communication)."""
+        return layout_from_counts(np.float32 if self.dtype_itemsize == 4 else np.float64, self.global_shape,
+                                  self.all_cube_words, r)
+
+    @property
+    def global_stream_words(self) -> int:
+        return self.global_header_words + self.total_cube_words + self.total_border
+
+    @property
+    def global_cube_offset(self) -> int:
+        return self.global_header_words + self.cube_word_base
+
+    @property
+    def global_border_offset(self) -> int:
+        return self.global_header_words + self.total_cube_words + self.border_base
+
+
+def exchange_layout(dtype, global_shape: Sequence[int], local_cube_words, group=None, device=None) -> ShardLayout:
+    """The exchange step: all-gather the per-rank compressed word counts and scan them.
+    ``local_cube_words`` is an int (host) or a one-element integer tensor (device; stays on device
+    until the gathered vector is read back once)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    spans = slab_partition(global_shape, world)
+    if isinstance(local_cube_words, torch.Tensor):
+        mine = local_cube_words.to(torch.int64).reshape(1)
+    else:
+        mine = torch.tensor([int(local_cube_words)], dtype=torch.int64, device=device or "cpu")
+    if world > 1:
+        gathered = torch.empty(world, dtype=torch.int64, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+    else:
+        gathered = mine
+    words = [int(w) for w in gathered.cpu().tolist()]
+    return layout_from_counts(dtype, global_shape, words, rank)
+
+
+def layout_from_counts(dtype, global_shape: Sequence[int], cube_words: Sequence[int], rank: int) -> ShardLayout:
+    world = len(cube_words)
+    spans = slab_partition(global_shape, world)
+    shapes = [slab_shape(global_shape, s) for s in spans]
+    cubes = [cubes_in(s) for s in shapes]
+    borders = [border_in(s) for s in shapes]
+    assert sum(cubes) == cubes_in(global_shape), "slabs must tile the cube grid"
+    assert sum(borders) == border_in(global_shape), "slab borders must tile the global border"
+    return ShardLayout(
+        rank=rank, world_size=world, local_shape=shapes[rank], local_cubes=cubes[rank],
+        cube_index_base=sum(cubes[:rank]), local_header_words=header_words(dtype, cubes[rank]),
+        local_cube_words=int(cube_words[rank]), local_border=borders[rank],
+        global_cubes=sum(cubes), global_header_words=header_words(dtype, sum(cubes)),
+        cube_word_base=int(sum(cube_words[:rank])), total_cube_words=int(sum(cube_words)),
+        border_base=sum(borders[:rank]), total_border=sum(borders),
+        global_shape=tuple(int(x) for x in global_shape), all_cube_words=tuple(int(w) for w in cube_words),
+        dtype_itemsize=np.dtype(dtype).itemsize)
+
+
+def stitch_global_stream(dtype, global_shape: Sequence[int], local_streams: Sequence[np.ndarray]) -> np.ndarray:
+    """Host-side assembly of the global stream from every rank's complete local stream (numpy, bits
+    dtype). Used for validation and by the CPU tests; on GPUs the same arithmetic drives the NVLink
+    gather (``gather_global_stream``)."""
+    bits = np.uint32 if np.dtype(dtype).itemsize == 4 else np.uint64
+    world = len(local_streams)
+    spans = slab_partition(global_shape, world)
+    shapes = [slab_shape(global_shape, s) for s in spans]
+    cubes = [cubes_in(s) for s in shapes]
+    borders = [border_in(s) for s in shapes]
+    hdrs = [header_words(dtype, c) for c in cubes]
+    cube_words = []
+    headers32 = []
+    for r, s in enumerate(local_streams):
+        s = np.ascontiguousarray(s, dtype=bits)
+        h32 = s[: hdrs[r]].view(np.uint32)[: cubes[r]]
+        cube_words.append(int(h32[-1]) if cubes[r] else 0)
+        headers32.append(h32)
+    layouts = [layout_from_counts(dtype, global_shape, cube_words, r) for r in range(world)]
+    out = np.zeros(layouts[0].global_stream_words, dtype=bits)
+    gh32 = out[: layouts[0].global_header_words].view(np.uint32)
+    for r, s in enumerate(local_streams):
+        L = layouts[r]
+        s = np.ascontiguousarray(s, dtype=bits)
+        gh32[L.cube_index_base: L.cube_index_base + L.local_cubes] = headers32[r] + np.uint32(L.cube_word_base)
+        out[L.global_cube_offset: L.global_cube_offset + L.local_cube_words] = s[hdrs[r]: hdrs[r] + L.local_cube_words]
+        b0 = hdrs[r] + L.local_cube_words
+        out[L.global_border_offset: L.global_border_offset + L.local_border] = s[b0: b0 + L.local_border]
+    return out
+
+
+def gather_global_stream(layout: ShardLayout, local_stream, fixed_header32, root: int = 0, group=None):
+    """Final stream gather over the process group (NCCL send/recv on NVLink; gloo in the CPU tests).
+    ``local_stream``: the rank's complete local stream tensor (bits held as int32 / int64);
+    ``fixed_header32``: int32 tensor with the rank's ``local_cubes`` GLOBAL header entries.
+    Returns the assembled global stream tensor on ``root`` (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = layout.world_size, layout.rank
+    hdr = layout.local_header_words
+    cubes_seg = local_stream[hdr: hdr + layout.local_cube_words]
+    border_seg = local_stream[hdr + layout.local_cube_words: hdr + layout.local_cube_words + layout.local_border]
+    out = None
+    ops = []
+    if rank == root:
+        out = torch.zeros(layout.global_stream_words, dtype=local_stream.dtype, device=local_stream.device)
+        header32 = out[: layout.global_header_words].view(torch.int32)
+        for r in range(world):
+            L = layout.peer(r)
+            h_dst = header32[L.cube_index_base: L.cube_index_base + L.local_cubes]
+            c_dst = out[L.global_cube_offset: L.global_cube_offset + L.local_cube_words]
+            b_dst = out[L.global_border_offset: L.global_border_offset + L.local_border]
+            if r == root:
+                h_dst.copy_(fixed_header32[: L.local_cubes])
+                c_dst.copy_(cubes_seg)
+                b_dst.copy_(border_seg)
+            else:
+                if L.local_cubes:
+                    ops.append(dist.P2POp(dist.irecv, h_dst, r, group))
+                if L.local_cube_words:
+                    ops.append(dist.P2POp(dist.irecv, c_dst, r, group))
+                if L.local_border:
+                    ops.append(dist.P2POp(dist.irecv, b_dst, r, group))
+    else:
+        if layout.local_cubes:
+            ops.append(dist.P2POp(dist.isend, fixed_header32[: layout.local_cubes].contiguous(), root, group))
+        if layout.local_cube_words:
+            ops.append(dist.P2POp(dist.isend, cubes_seg.contiguous(), root, group))
+        if layout.local_border:
+            ops.append(dist.P2POp(dist.isend, border_seg.contiguous(), root, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out

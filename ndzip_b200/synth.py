@@ -80,19 +80,33 @@ def engineered_cube(bits_dtype, seed: int = 7) -> np.ndarray:
     return w.reshape(-1).copy()
 
 
-def smooth(shape, dtype, seed: int = 0x5EED0002, noise: float = 1e-4) -> np.ndarray:
-    """Turbulence-like field: six k^(-5/3) sine modes with hashed directions/phases + small noise
-    (SURVEY.md §8d item 1). Evaluated in float64, rounded to ``dtype``. Mid-range ratios."""
-    dims = len(shape)
-    consts = splitmix64(np.arange(64, dtype=np.uint64) ^ (np.uint64(seed) << np.uint64(32)))
+def smooth_constants(seed: int, dims: int, modes: int = 6):
+    """(amplitude, integer wave vector, phase) per mode — shared with bench.py's device generator."""
+    consts = splitmix64(np.arange(8 * (modes + 1), dtype=np.uint64) ^ (np.uint64(seed) << np.uint64(32)))
     u01 = (consts >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+    out = []
+    for k in range(1, modes + 1):
+        wave = [float(np.floor(u01[8 * k + 1 + d] * (k + 1))) for d in range(dims)]  # components 0..k
+        if not any(wave):
+            wave[-1] = float(k)
+        out.append((k ** (-5.0 / 3.0), wave, 2 * np.pi * float(u01[8 * k])))
+    return out
+
+
+def smooth(shape, dtype, seed: int = 0x5EED0002, noise: float = 1e-4) -> np.ndarray:
+    """Turbulence-like field: six sine modes with a k^(-5/3) amplitude
+    spectrum, hashed integer wave vectors |m_d| <= k and phases, plus `noise` * u(index), u in [-1,1).
+    Evaluated in float64, rounded to ``dtype``. Mid-range ratios (~0.6 for 3D float32)."""
+    dims = len(shape)
     n = _count(shape)
+    if n == 0:
+        return np.zeros(shape, dtype=dtype)
+    modes = smooth_constants(seed, dims)
     out = np.zeros(n, dtype=np.float64)
-    # process in slabs to bound temporary memory
-    step = 1 << 22
     strides = [1] * dims
     for d in range(dims - 2, -1, -1):
         strides[d] = strides[d + 1] * int(shape[d + 1])
+    step = 1 << 22  # slabs bound the temporaries
     for lo in range(0, n, step):
         idx = np.arange(lo, min(n, lo + step), dtype=np.uint64)
         coords = []
@@ -101,13 +115,12 @@ def smooth(shape, dtype, seed: int = 0x5EED0002, noise: float = 1e-4) -> np.ndar
             coords.append((rem // np.uint64(strides[d])).astype(np.float64) / float(shape[d]))
             rem = rem % np.uint64(strides[d])
         acc = np.zeros(idx.size, dtype=np.float64)
-        for k in range(1, 7):
-            phase = 2 * np.pi * u01[8 * k]
+        for amp, wave, phase in modes:
             arg = np.zeros(idx.size, dtype=np.float64)
             for d in range(dims):
-                direction = np.floor(u01[8 * k + 1 + d] * 3.0) + 1.0  # 1..3 whole periods scale
-                arg += direction * coords[d]
-            acc += k ** (-5.0 / 3.0) * np.sin(2 * np.pi * k * arg + phase)
+                if wave[d]:
+                    arg += wave[d] * coords[d]
+            acc += amp * np.sin(2 * np.pi * arg + phase)
         jitter = (splitmix64(idx ^ (np.uint64(seed) << np.uint64(32))) >> np.uint64(11)).astype(np.float64) * 2.0 ** -52 - 1.0
         out[lo:lo + idx.size] = acc + noise * jitter
     return out.astype(dtype).reshape(shape)

@@ -1,0 +1,93 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds/loads, exports every symbol that
+include/ndzip_b200.h declares, its host-side stream arithmetic matches the oracle, and the compute
+entry points fail loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ndzip_b200 import build as nzbuild
+    from ndzip_b200 import _lib
+    nzbuild.build()  # no-op when up to date
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    header = open(os.path.join(ROOT, "include", "ndzip_b200.h")).read()
+    declared = set(re.findall(r"\b(ndzb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ndzb_status"}
+    assert len(declared) >= 18
+    raw = ctypes.CDLL(os.path.join(ROOT, "ndzip_b200", "libndzip_b200.so"))
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in include/ndzip_b200.h but not exported"
+    from ndzip_b200 import _lib
+    assert declared == {s[0] for s in _lib.SYMBOLS}
+
+
+def test_no_product_dependency_on_oracle():
+    # the product package must never import or link the checkers
+    pkg = os.path.join(ROOT, "ndzip_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "ndzip_oracle" not in text and "libndzip_ref" not in text, f
+
+
+SHAPES = [(0,), (1,), (4095,), (4096,), (3 * 4096 + 5,), (63, 64), (64, 64), (255, 255), (130, 64), (70, 10),
+          (16, 16, 16), (63, 63, 63), (33, 16, 48), (9, 40, 40), (512, 512, 512), (1 << 24,), (8192, 8192)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_host_arithmetic_matches_oracle(lib, oracle, shape):
+    import ndzip_b200 as nz
+    from ndzip_b200 import _lib
+    dims, sz = _lib.size3(shape)
+    assert nz.num_hypercubes(shape) == oracle.num_hypercubes(shape)
+    assert lib.ndzb_border_element_count(dims, sz) == oracle.border_element_count(shape)
+    for dtype in ("float32", "float64"):
+        assert nz.compressed_length_bound(dtype, shape) == oracle.compressed_length_bound(dtype, shape)
+    H = nz.num_hypercubes(shape)
+    assert lib.ndzb_header_words(0, H) == H
+    assert lib.ndzb_header_words(1, H) == (H + 1) // 2
+    assert lib.ndzb_compressed_cube_bound(0) == 4224 and lib.ndzb_compressed_cube_bound(1) == 4160
+
+
+def test_bound_matches_reference(lib, reference):
+    import ndzip_b200 as nz
+    for shape in SHAPES:
+        if int(np.prod(shape)) == 0:
+            continue
+        for dtype in ("float32", "float64"):
+            assert nz.compressed_length_bound(dtype, shape) == reference.compressed_length_bound(dtype, shape)
+
+
+def test_compute_fails_loudly_without_a_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import ndzip_b200 as nz
+    with pytest.raises(nz.NdzipB200Error, match="CUDA"):
+        nz.make_cuda_compressor("float32", (64, 64))
+    with pytest.raises(nz.NdzipB200Error, match="CUDA"):
+        nz.make_cuda_offloader("float64", 3)
+
+
+def test_argument_errors_mirror_the_reference(lib):
+    import ndzip_b200 as nz
+    with pytest.raises(nz.NdzipB200Error):
+        nz.compressor_requirements([(4, 4), (4,)])          # reference src/ndzip/common.cc:12-15
+    with pytest.raises(nz.NdzipB200Error, match="empty requirements"):
+        nz.compressor_requirements().dimensions              # reference src/ndzip/common.hh:319-322
+    with pytest.raises(nz.NdzipB200Error, match="dimensionality"):
+        nz.num_hypercubes((2, 2, 2, 2))                      # reference src/ndzip/common.hh:642
+    assert lib.ndzb_strerror(-2).decode().startswith("data dimensionality does not match")
+    assert b"sm_100a" in lib.ndzb_version()

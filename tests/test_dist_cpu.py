@@ -1,0 +1,92 @@
+"""Host-side logic of the multi-GPU path on CPU: slab partitioning, the cross-rank offset exchange
+(all_gather + exclusive scan) and the stream gather, with world_size 2 and 3 over ``gloo``.
+Per-rank compression is done by the oracle here (test infrastructure); on GPUs the same host logic
+wraps the CUDA path (bench.py, tests/test_gpu_parity.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from ndzip_b200 import dist as nzd
+from ndzip_b200 import synth
+
+CASES = [
+    ("float32", (5 * 4096 + 100,)),
+    ("float32", (200, 130)),
+    ("float64", (67, 40, 50)),
+    ("float64", (3 * 4096,)),
+    ("float32", (48, 32, 32)),
+]
+
+
+def test_slab_partition_properties():
+    for shape in [(4096 * 9 + 5,), (1000, 64), (16 * 7 + 3, 16, 16), (15, 64, 64), (64, 64, 64)]:
+        side = nzd.SIDE[len(shape)]
+        for world in (1, 2, 3, 8):
+            spans = nzd.slab_partition(shape, world)
+            assert spans[0][0] == 0 and spans[-1][1] == shape[0]
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(s[1] % side == 0 for s in spans[:-1])
+            assert sum(nzd.cubes_in(nzd.slab_shape(shape, s)) for s in spans) == nzd.cubes_in(shape)
+            assert sum(nzd.border_in(nzd.slab_shape(shape, s)) for s in spans) == nzd.border_in(shape)
+            counts = [nzd.cubes_in(nzd.slab_shape(shape, s)) for s in spans]
+            assert max(counts) - min(counts) <= nzd.cubes_in((side,) + tuple(shape[1:]))
+
+
+@pytest.mark.parametrize("dtype,shape", CASES)
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_stitched_shards_equal_global_stream(oracle, dtype, shape, world):
+    data = synth.hashed(shape, dtype, seed=31)
+    expect = oracle.compress(data)
+    spans = nzd.slab_partition(shape, world)
+    local = [oracle.compress(np.ascontiguousarray(data[b:e])) for b, e in spans]
+    got = nzd.stitch_global_stream(dtype, shape, local)
+    assert got.size == expect.size
+    assert np.array_equal(got, expect)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, dtype, shape, result_dir):
+    import torch
+    import torch.distributed as dist
+    from oracle import get_oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        oracle = get_oracle()
+        data = synth.hashed(shape, dtype, seed=31)
+        b, e = nzd.slab_partition(shape, world)[rank]
+        local = oracle.compress(np.ascontiguousarray(data[b:e]))
+        cubes = nzd.cubes_in(nzd.slab_shape(shape, (b, e)))
+        hdr = nzd.header_words(dtype, cubes)
+        local_words = int(local[:hdr].view(np.uint32)[cubes - 1]) if cubes else 0
+        layout = nzd.exchange_layout(dtype, shape, local_words)
+        assert layout.local_cubes == cubes and layout.local_cube_words == local_words
+        tdt = torch.int32 if np.dtype(dtype).itemsize == 4 else torch.int64
+        t_local = torch.from_numpy(local.view(np.int32 if tdt == torch.int32 else np.int64).copy())
+        header32 = t_local[:hdr].view(torch.int32)[:cubes].clone()
+        header32 += layout.cube_word_base  # the header fix-up (ndzb_add_offset on the GPU)
+        out = nzd.gather_global_stream(layout, t_local, header32, root=0)
+        if rank == 0:
+            np.save(os.path.join(result_dir, "global.npy"), out.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype,shape", CASES[:3])
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_offset_exchange_and_gather(oracle, tmp_path, dtype, shape, world):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, dtype, shape, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(os.path.join(str(tmp_path), "global.npy"))
+    bits = np.uint32 if dtype == "float32" else np.uint64
+    expect = oracle.compress(synth.hashed(shape, dtype, seed=31))
+    assert np.array_equal(got.view(bits), expect)

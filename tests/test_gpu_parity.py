@@ -1,0 +1,305 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) against the oracle, the committed golden
+fixtures and — where oracle/_ref/libndzip_ref.so travelled with the repo — the unmodified reference
+CPU codec. Bit-exact everywhere: this is integer work.
+
+Mirrors the reference's own parity tests (src/test/codec_profile_test.inl): identical
+streams between encoders for one cube (:952-995), for bordered shapes (:37-140), 0-hypercube extents
+(:1045-1082), decode(encode(x)) == x for every encoder/decoder pairing.
+"""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from ndzip_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIDE = {1: 4096, 2: 64, 3: 16}
+PROFILES = [(dt, d) for dt in ("float32", "float64") for d in (1, 2, 3)]
+PATHS = ["tma", "vec16", "scalar"]
+
+
+def _rows():
+    with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
+        return json.load(f)["rows"]
+
+
+def _row_id(r):
+    return f"{r['generator']}-{r['dtype']}-{'x'.join(map(str, r['shape']))}"
+
+
+@pytest.fixture(scope="module")
+def nz():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import ndzip_b200
+    from ndzip_b200 import _lib
+    _lib.load()  # fails loudly if the extension is missing
+    return ndzip_b200
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("row", _rows(), ids=_row_id)
+def test_golden_fixture(nz, row, path):
+    from gpu_util import gpu_compress, gpu_decompress, load_path
+    shape = tuple(row["shape"])
+    data = synth.make(row["generator"], shape, row["dtype"], **row["kwargs"])
+    assert nz.compressed_length_bound(row["dtype"], shape) == row["bound"]
+    with load_path(path):
+        stream, _ = gpu_compress(data)
+    assert stream.size == row["stream_words"]
+    assert "%08x" % zlib.crc32(stream.tobytes()) == row["stream_crc32"]
+    assert ["%x" % int(w) for w in stream[:4]] == row["first_words"]
+    back = gpu_decompress(stream, row["dtype"], shape)
+    assert back.tobytes() == data.tobytes()
+
+
+@pytest.mark.parametrize("dtype,dims", PROFILES)
+def test_golden_single_cube_streams(nz, dtype, dims):
+    # word-by-word comparison against streams produced by the reference CPU encoder
+    from gpu_util import gpu_compress
+    cubes = np.load(os.path.join(ROOT, "tests", "golden", "cubes.npz"))
+    data = synth.hashed((SIDE[dims],) * dims, dtype, seed=11)
+    data.reshape(-1)[: (32 if dtype == "float32" else 64)] = 0
+    expect = cubes[f"{dtype}_{dims}d_stream"]
+    stream, _ = gpu_compress(data)
+    assert stream.size == expect.size
+    mismatch = np.nonzero(stream != expect)[0]
+    assert mismatch.size == 0, f"first mismatching word {mismatch[:8]}"
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("gen", ["hashed", "raw_bits", "quantised", "poly", "smooth"])
+@pytest.mark.parametrize("dtype,dims", PROFILES)
+def test_stream_equals_oracle(nz, oracle, dtype, dims, gen, path):
+    from gpu_util import gpu_compress, gpu_decompress, load_path
+    n = {1: 5 * 4096 + 123, 2: 4 * 64 - 1, 3: 4 * 16 - 1}[dims]  # bordered (codec_profile_test.inl:44-50)
+    shape = (n,) * dims
+    kw = {} if gen in ("poly",) else {"seed": 77}
+    data = synth.make(gen, shape, dtype, **kw)
+    data.reshape(-1)[: (32 if dtype == "float32" else 64)] = 0  # regression: first chunk zero (:54-58)
+    expect = oracle.compress(data)
+    with load_path(path):
+        stream, full = gpu_compress(data)
+    assert stream.size == expect.size
+    assert np.array_equal(stream, expect)
+    back = gpu_decompress(expect, dtype, shape)  # GPU decodes the CPU stream
+    assert back.tobytes() == data.tobytes()
+    back_cpu, consumed = oracle.decompress(stream, dtype, shape)  # CPU decodes the GPU stream
+    assert consumed == stream.size and back_cpu.tobytes() == data.tobytes()
+
+
+@pytest.mark.parametrize("dtype,dims", PROFILES)
+def test_aligned_multi_cube_equals_reference(nz, oracle, dtype, dims):
+    # no border, many cubes, TMA path; compared against the unmodified reference when present
+    from oracle import get_reference
+    from gpu_util import gpu_compress, gpu_decompress
+    shape = {1: (64 * 4096,), 2: (512, 768), 3: (64, 96, 128)}[dims]
+    data = synth.smooth(shape, dtype, seed=5)
+    ref = get_reference()
+    expect = ref.compress(data, threads=0) if ref is not None else oracle.compress(data)
+    stream, _ = gpu_compress(data)
+    assert np.array_equal(stream, expect)
+    assert gpu_decompress(stream, dtype, shape).tobytes() == data.tobytes()
+
+
+@pytest.mark.parametrize("dtype,dims", PROFILES)
+@pytest.mark.parametrize("n", [0, 1])
+def test_zero_hypercube_extents(nz, oracle, dtype, dims, n):
+    # reference src/test/codec_profile_test.inl:1045-1082
+    from gpu_util import gpu_compress, gpu_decompress
+    shape = (n,) * dims
+    data = synth.ramp(shape, dtype) + np.dtype(dtype).type(1.5)
+    stream, _ = gpu_compress(data)
+    assert np.array_equal(stream, oracle.compress(data))
+    assert stream.size == data.size
+    assert gpu_decompress(stream, dtype, shape).tobytes() == data.tobytes()
+
+
+def test_header_padding_word_is_zero(nz):
+    # f64 with an odd cube count: the GPU encoders write 0 to the padding word (cuda_codec.inl:446-452)
+    from gpu_util import gpu_compress
+    data = synth.hashed((3 * 4096,), "float64", seed=2)
+    stream, full = gpu_compress(data, fill=0xFF)
+    header = stream[:2].view(np.uint32)
+    assert header[3] == 0
+    assert header[2] == stream.size - 2
+
+
+def test_context_reuse_and_varying_extents(nz, oracle):
+    # one compressor object, many calls (epoch / ticket bookkeeping), as the CLI does per chunk
+    from gpu_util import gpu_compress
+    req = nz.compressor_requirements([(96, 96, 96), (33, 50, 70), (16, 16, 16)])
+    comp = nz.make_cuda_compressor("float32", req)
+    for rep in range(3):
+        for shape in [(96, 96, 96), (16, 16, 16), (33, 50, 70), (48, 64, 80)]:
+            data = synth.hashed(shape, "float32", seed=10 + rep)
+            stream, _ = gpu_compress(data, compressor=comp)
+            assert np.array_equal(stream, oracle.compress(data)), (rep, shape)
+
+
+def test_context_grows_beyond_requirements(nz, oracle):
+    from gpu_util import gpu_compress
+    comp = nz.make_cuda_compressor("float64", nz.compressor_requirements((64, 64)))
+    data = synth.poly((256, 320), "float64")
+    stream, _ = gpu_compress(data, compressor=comp)
+    assert np.array_equal(stream, oracle.compress(data))
+
+
+def test_length_pointer_is_optional(nz, oracle):
+    from gpu_util import gpu_compress
+    data = synth.quantised((130, 200), "float32", seed=4)
+    _, full = gpu_compress(data, want_length_tensor=False)
+    expect = oracle.compress(data)
+    assert np.array_equal(full[: expect.size], expect)
+
+
+def test_unaligned_device_pointer_uses_fallback_path(nz, oracle):
+    import torch
+    import ndzip_b200 as nzb
+    shape = (32, 32, 48)
+    data = synth.hashed(shape, "float32", seed=6)
+    backing = torch.zeros(data.size + 1, dtype=torch.float32, device="cuda")
+    view = backing[1:]  # 4-byte aligned only: TMA and 16-byte loads are impossible
+    view.copy_(torch.from_numpy(data.reshape(-1)))
+    bound = nzb.compressed_length_bound("float32", shape)
+    out_backing = torch.zeros(bound + 1, dtype=torch.int32, device="cuda")
+    d_len = torch.zeros(1, dtype=torch.int32, device="cuda")
+    comp = nzb.make_cuda_compressor("float32", shape)
+    comp.compress(view, shape, out_backing[1:], d_len)
+    torch.cuda.synchronize()
+    n = int(d_len.item())
+    got = out_backing[1:1 + n].cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, oracle.compress(data))
+    dec = nzb.make_cuda_decompressor("float32", 3)
+    back = torch.zeros(data.size + 1, dtype=torch.float32, device="cuda")
+    dec.decompress(out_backing[1:], back[1:], shape)
+    torch.cuda.synchronize()
+    assert back[1:].cpu().numpy().tobytes() == data.tobytes()
+
+
+def test_dimension_mismatch_raises(nz):
+    import torch
+    comp = nz.make_cuda_compressor("float32", (64, 64))
+    x = torch.zeros(4096, device="cuda")
+    out = torch.zeros(8192, dtype=torch.int32, device="cuda")
+    with pytest.raises(nz.NdzipB200Error, match="dimensionality"):
+        comp.compress(x, (4096,), out, None)  # reference cuda_codec.inl:557-559
+    with pytest.raises(nz.NdzipB200Error):
+        nz.compressor_requirements([(4, 4), (4,)])  # reference common.cc:12-15
+    with pytest.raises(nz.NdzipB200Error, match="empty requirements"):
+        nz.make_cuda_compressor("float32", nz.compressor_requirements())
+
+
+@pytest.mark.parametrize("dtype,dims", PROFILES)
+def test_offloader_host_api(nz, oracle, dtype, dims):
+    # reference include/ndzip/offload.hh:16-24; tests use it at codec_profile_test.inl:64-93
+    shape = {1: (3 * 4096 + 17,), 2: (200, 130), 3: (40, 33, 50)}[dims]
+    data = synth.smooth(shape, dtype, seed=9)
+    off = nz.make_cuda_offloader(dtype, dims)
+    bits = np.uint32 if dtype == "float32" else np.uint64
+    stream = np.zeros(nz.compressed_length_bound(dtype, shape), dtype=bits)
+    n = off.compress(data, shape, stream)
+    assert off.kernel_duration_ns is not None and off.kernel_duration_ns > 0
+    expect = oracle.compress(data)
+    assert n == expect.size and np.array_equal(stream[:n], expect)
+    back = np.zeros(shape, dtype=dtype)
+    consumed = off.decompress(stream, n, back, shape)
+    assert consumed == n
+    assert back.tobytes() == data.tobytes()
+
+
+def test_sharded_cube_ranges_stitch_to_the_full_stream(nz, oracle):
+    # single-GPU check of the multi-GPU building blocks
+    import torch
+    shape = (64, 48, 80)
+    dtype = "float32"
+    data = synth.smooth(shape, dtype, seed=12)
+    expect = oracle.compress(data)
+    H = nz.num_hypercubes(shape)
+    d_in = torch.from_numpy(data).cuda()
+    comp = nz.make_cuda_compressor(dtype, shape)
+    bounds = [0, H // 3, H // 3, H - 5, H]
+    pieces, offsets, totals = [], [], []
+    for b, e in zip(bounds[:-1], bounds[1:]):
+        cubes = torch.zeros(max(1, (e - b) * 4224), dtype=torch.int32, device="cuda")
+        offs = torch.zeros(max(1, e - b), dtype=torch.int32, device="cuda")
+        tot = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+        comp.compress_cubes(d_in.data_ptr(), shape, b, e, cubes, offs, tot)
+        torch.cuda.synchronize()
+        t = int(tot.item())
+        pieces.append(cubes[:t].cpu().numpy().view(np.uint32))
+        offsets.append(offs[: e - b].cpu().numpy().view(np.uint32))
+        totals.append(t)
+    base = np.concatenate([[0], np.cumsum(totals)[:-1]]).astype(np.uint32)
+    header = np.concatenate([o + b for o, b in zip(offsets, base)])
+    stitched = np.concatenate([header] + pieces)
+    assert np.array_equal(stitched, expect[: stitched.size])
+    # ranged decompression of the full stream
+    dec = nz.make_cuda_decompressor(dtype, 3)
+    d_stream = torch.from_numpy(expect.view(np.int32).copy()).cuda()
+    out = torch.zeros(data.size, dtype=torch.float32, device="cuda")
+    for b, e in zip(bounds[:-1], bounds[1:]):
+        dec.decompress_cubes(d_stream, out.data_ptr(), shape, b, e)
+    torch.cuda.synchronize()
+    assert out.cpu().numpy().tobytes() == data.tobytes()
+
+
+# ------------------------------------------------------------------ BASELINE.json sizes
+# Full-size configs: stream equality against the unmodified reference (multi-threaded) when it
+# travelled with the repo, plus size-independent properties otherwise.
+
+BASELINE_CASES = [
+    ("float32", (1 << 24,)),            # config 1: 1D fp32 16 Mi
+    ("float32", (512, 512, 512)),       # config 2: 3D fp32 512^3
+    ("float64", (8192, 8192)),          # config 3: 2D fp64 8192^2
+]
+
+
+@pytest.mark.parametrize("dtype,shape", BASELINE_CASES, ids=["cfg1-1d-f32-16Mi", "cfg2-3d-f32-512", "cfg3-2d-f64-8192"])
+def test_baseline_config_roundtrip_and_reference_parity(nz, dtype, shape):
+    import torch
+    from bench import make_device_input  # same generator the benchmark uses
+    from oracle import get_reference
+    d_in = make_device_input(dtype, shape, seed=0x5EED0002)
+    bound = nz.compressed_length_bound(dtype, shape)
+    tbits = torch.int32 if dtype == "float32" else torch.int64
+    d_stream = torch.empty(bound, dtype=tbits, device="cuda")
+    d_len = torch.zeros(1, dtype=torch.int32, device="cuda")
+    comp = nz.make_cuda_compressor(dtype, shape)
+    comp.compress(d_in, shape, d_stream, d_len)
+    torch.cuda.synchronize()
+    n = int(d_len.cpu().numpy().view(np.uint32)[0])
+    H = nz.num_hypercubes(shape)
+    hdr_words = H if dtype == "float32" else (H + 1) // 2
+    header = d_stream[:hdr_words].cpu().numpy().view(np.uint32)[:H].astype(np.int64)
+    # properties: offsets strictly increase by [C, bound] per cube; length = header + last offset
+    steps = np.diff(np.concatenate([[0], header]))
+    C, cube_bound = (128, 4224) if dtype == "float32" else (64, 4160)
+    assert steps.min() >= C and steps.max() <= cube_bound
+    assert n == hdr_words + int(header[-1])
+    # round trip on the device
+    dec = nz.make_cuda_decompressor(dtype, len(shape))
+    d_back = torch.empty_like(d_in)
+    dec.decompress(d_stream, d_back, shape)
+    torch.cuda.synchronize()
+    assert torch.equal(d_in.view(tbits), d_back.view(tbits))
+    # second compression into a fresh buffer is bit-identical (determinism despite dynamic scheduling)
+    d_stream2 = torch.empty(bound, dtype=tbits, device="cuda")
+    comp.compress(d_in, shape, d_stream2, d_len)
+    torch.cuda.synchronize()
+    assert torch.equal(d_stream[:n], d_stream2[:n])
+    ref = get_reference()
+    if ref is not None:
+        host = d_in.cpu().numpy()
+        bits = np.uint32 if dtype == "float32" else np.uint64
+        expect = np.zeros(bound, dtype=bits)
+        n_ref = ref.compress_into(host, expect, threads=0)
+        assert n_ref == n
+        got = d_stream[:n].cpu().numpy().view(bits)
+        assert zlib.crc32(got.tobytes()) == zlib.crc32(expect[:n].tobytes())
+        assert np.array_equal(got, expect[:n])
