@@ -122,53 +122,61 @@ def make_device_input(dtype, shape, seed=SEED, noise=1e-4, device="cuda", index_
 # clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and clock-event reasons through NVML every few ms while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
-    def __init__(self, gpu_index=0):
-        self.gpu_index = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index=0, period_s=0.004):
+        self.gpu_index, self.period_s = gpu_index, period_s
+        self.samples, self.reason_bits, self.power = [], 0, []
+        self._stop = threading.Event()
+        self.thread = None
+        self.handle = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:  # CUDA_VISIBLE_DEVICES-proof: look the device up by PCI bus id
+                bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id
+                dom = torch.cuda.get_device_properties(gpu_index).pci_domain_id
+                dev = torch.cuda.get_device_properties(gpu_index).pci_device_id
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0")
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml = pynvml
+        except Exception:
+            self.handle = None
+
+    def _loop(self):
+        nv = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    self.reason_bits |= nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    self.reason_bits |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(self.period_s)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+        if self.handle is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.handle is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self._stop.set()
+        self.thread.join(timeout=2)
         try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            mx = self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.reason_bits & bit)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": mx,
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None, "reasons": reasons}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -232,9 +240,11 @@ def run_cpu_reference(dtype, shape, data, steps, warmup, threads=0):
             if it >= warmup:
                 times_c.append(t1 - t0)
                 times_d.append(t2 - t1)
-        assert back.tobytes() == data.tobytes(), "reference CPU round trip failed"
+        # The reference's OpenMP compressor has a data race (cpu_codec.inl:826-836) that occasionally
+        # corrupts its own stream; timing is unaffected, so this is recorded rather than fatal.
+        roundtrip_ok = back.tobytes() == data.tobytes()
     else:
-        kind, cores = "port", 1
+        kind, cores, roundtrip_ok = "port", 1, True
         oracle = get_oracle()
         for it in range(max(1, warmup // 3) + max(1, steps // 3)):
             t0 = time.perf_counter()
@@ -251,14 +261,14 @@ def run_cpu_reference(dtype, shape, data, steps, warmup, threads=0):
         "kind": kind, "cores": int(cores), "value": nbytes / (tc + td) / 1e9,
         "compress_gbs": nbytes / tc / 1e9, "decompress_gbs": nbytes / td / 1e9,
         "ratio": n * np.dtype(bits).itemsize / nbytes, "ms_per_step": (tc + td) * 1e3,
-        "steps": len(times_c),
+        "steps": len(times_c), "roundtrip_ok": bool(roundtrip_ok),
     }
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -386,7 +396,7 @@ def main():
             ts.append(a.elapsed_time(b))
         return ts
 
-    reps = max(5, args.steps)
+    reps = max(5, min(args.steps, 20))
     tc = time_call(lambda: comp.compress(d_in, shape, d_stream, d_len), reps)
     td = time_call(lambda: dec.decompress(d_stream, d_back, shape), reps)
     clocks = sampler.stop() if rank == 0 else None

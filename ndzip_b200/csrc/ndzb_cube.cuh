@@ -172,33 +172,72 @@ struct alignas(16) quad { uint32_t x, y, z, w; };
 NDZB_HD quad ld_quad(const uint32_t *p) { return *reinterpret_cast<const quad *>(p); }
 NDZB_HD void st_quad(uint32_t *p, quad q) { *reinterpret_cast<quad *>(p) = q; }
 
+// Input-tile layout of the compress kernel, per profile. A run is two half-runs of 16 values:
+//   float 1D/2D : the run is one 128-byte row, half h = units 4h..4h+3              (SWIZZLE_128B)
+//   float 3D    : a half-run is one 16-element x-row = 64 bytes; even-y rows live in region 0, odd-y
+//                 rows in region 1 (8 KiB each, 64-byte rows, units XORed with (row>>1)&3 =
+//                 CU_TENSOR_MAP_SWIZZLE_64B). TMA cannot lay a 64-byte inner box densely under
+//                 SWIZZLE_128B, and with one region per y parity the eight lanes of a quarter-warp
+//                 read eight consecutive rows, which the 64-byte swizzle spreads over all banks.
+//   double      : half h = row u of region h (16 KiB each, 128-byte rows)            (SWIZZLE_128B)
+template<typename Bits, int Dims>
+struct input_layout {
+    static constexpr bool split64 = sizeof(Bits) == 4 && Dims == 3;
+    static constexpr int units_per_half = sizeof(Bits) == 4 ? 4 : 8;
+    static constexpr int region_words = sizeof(Bits) == 8 ? 4096 : 2048;  // only used when halves are regions
+
+    // 32-bit word index of 16-byte unit k of half-run `half` of run `run`
+    static NDZB_HD int half_unit(int run, int half, int k) {
+        if constexpr (sizeof(Bits) == 8) {
+            return half * region_words + tile_unit(run, k);
+        } else if constexpr (split64) {
+            return half * region_words + (run << 4) + ((k ^ ((run >> 1) & 3)) << 2);
+        } else {
+            return tile_unit(run, half * 4 + k);
+        }
+    }
+    // 32-bit word index (low word) of cube-local element e
+    static NDZB_HD int elem(int e) {
+        const int run = e >> 5, j = e & 31;
+        if constexpr (sizeof(Bits) == 8) {
+            return half_unit(run, j >> 4, (j & 15) >> 1) + ((j & 1) << 1);
+        } else {
+            return half_unit(run, j >> 4, (j & 15) >> 2) + (j & 3);
+        }
+    }
+};
+
 // Half-run `half` (16 values) of run `run`, bit-cast and rotated left by one (the reference fuses
 // the same rotate into its load, cuda_codec.inl:51-55).
+template<typename L>
 NDZB_HD void load_half_rot(const uint32_t *tile, int run, int half, uint32_t *out) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const quad q = ld_quad(tile + tile_unit(run, half * 4 + k));
+        const quad q = ld_quad(tile + L::half_unit(run, half, k));
         out[4 * k + 0] = rotl1(q.x);
         out[4 * k + 1] = rotl1(q.y);
         out[4 * k + 2] = rotl1(q.z);
         out[4 * k + 3] = rotl1(q.w);
     }
 }
+template<typename L>
 NDZB_HD void load_half_rot(const uint32_t *tile, int run, int half, uint64_t *out) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const quad q = ld_quad(tile + (half << 12) + tile_unit(run, k));
+        const quad q = ld_quad(tile + L::half_unit(run, half, k));
         out[2 * k + 0] = rotl1((static_cast<uint64_t>(q.y) << 32) | q.x);
         out[2 * k + 1] = rotl1((static_cast<uint64_t>(q.w) << 32) | q.z);
     }
 }
 
 // Last element (31) of run `run`, rotated.
+template<typename L>
 NDZB_HD uint32_t load_last_rot(const uint32_t *tile, int run, uint32_t) {
-    return rotl1(tile[tile_unit(run, 7) + 3]);
+    return rotl1(tile[L::elem(32 * run + 31)]);
 }
+template<typename L>
 NDZB_HD uint64_t load_last_rot(const uint32_t *tile, int run, uint64_t) {
-    const int w = (1 << 12) + tile_unit(run, 7) + 2;
+    const int w = L::elem(32 * run + 31);
     return rotl1((static_cast<uint64_t>(tile[w + 1]) << 32) | tile[w]);
 }
 
@@ -220,25 +259,26 @@ NDZB_HD void sub16(Bits *a, const Bits *b) {
 
 template<typename Bits, int Dims>
 NDZB_HD void residual_run(const uint32_t *tile, int u, Bits *r) {
+    using L = input_layout<Bits, Dims>;
     Bits *lo = r, *hi = r + 16;
-    load_half_rot(tile, u, 0, lo);
-    load_half_rot(tile, u, 1, hi);
+    load_half_rot<L>(tile, u, 0, lo);
+    load_half_rot<L>(tile, u, 1, hi);
     Bits left = 0;  // value preceding r[0] along x after the higher-axis differences
 
     if constexpr (Dims == 1) {
         // run u = elements [32u, 32u+32) of the 4096-long line
-        if (u > 0) left = load_last_rot(tile, u - 1, Bits{});
+        if (u > 0) left = load_last_rot<L>(tile, u - 1, Bits{});
     } else if constexpr (Dims == 2) {
         // 64 x 64: run u = row y = u>>1, columns [32g, 32g+32) with g = u&1; the row above is run u-2
         const int y = u >> 1, g = u & 1;
-        if (g) left = load_last_rot(tile, u - 1, Bits{});
+        if (g) left = load_last_rot<L>(tile, u - 1, Bits{});
         if (y > 0) {
             Bits up[16];
-            load_half_rot(tile, u - 2, 0, up);
+            load_half_rot<L>(tile, u - 2, 0, up);
             sub16(lo, up);
-            load_half_rot(tile, u - 2, 1, up);
+            load_half_rot<L>(tile, u - 2, 1, up);
             sub16(hi, up);
-            if (g) left -= load_last_rot(tile, u - 3, Bits{});
+            if (g) left -= load_last_rot<L>(tile, u - 3, Bits{});
         }
     } else {
         // 16^3: run u = rows y = 2p, 2p+1 of plane z, with z = u>>3, p = u&7.
@@ -247,15 +287,15 @@ NDZB_HD void residual_run(const uint32_t *tile, int u, Bits *r) {
         Bits above[16];  // row 2p-1 of plane z (after the z difference)
 #pragma unroll
         for (int i = 0; i < 16; ++i) above[i] = 0;
-        if (p > 0) load_half_rot(tile, u - 1, 1, above);
+        if (p > 0) load_half_rot<L>(tile, u - 1, 1, above);
         if (z > 0) {
             Bits back[16];
-            load_half_rot(tile, u - 8, 0, back);
+            load_half_rot<L>(tile, u - 8, 0, back);
             sub16(lo, back);
-            load_half_rot(tile, u - 8, 1, back);
+            load_half_rot<L>(tile, u - 8, 1, back);
             sub16(hi, back);
             if (p > 0) {
-                load_half_rot(tile, u - 9, 1, back);
+                load_half_rot<L>(tile, u - 9, 1, back);
                 sub16(above, back);
             }
         }

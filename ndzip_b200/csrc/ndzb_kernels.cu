@@ -130,9 +130,14 @@ __device__ __forceinline__ void issue_tma_load(
             const uint32_t cy = hc / g.cubes[2], cx = hc % g.cubes[2];
             ptx::tma_load_3d(slot, map, bar, 0, static_cast<int>(cx * 2), static_cast<int>(cy * 64));
         } else {
+            // two 8 KiB regions: even-y rows, odd-y rows (view [z][y/2][y parity][x], SWIZZLE_64B)
             const uint32_t cx = hc % g.cubes[2], t = hc / g.cubes[2];
             const uint32_t cy = t % g.cubes[1], cz = t / g.cubes[1];
-            ptx::tma_load_3d(slot, map, bar, static_cast<int>(cx * 16), static_cast<int>(cy * 16), static_cast<int>(cz * 16));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                ptx::tma_load_4d(slot + h * input_layout<uint32_t, 3>::region_words, map, bar, static_cast<int>(cx * 16), h,
+                        static_cast<int>(cy * 8), static_cast<int>(cz * 16));
+            }
         }
     } else {
         // two 16 KiB regions: region h holds the h-th 16-value half of every run
@@ -156,6 +161,7 @@ __device__ __forceinline__ void issue_tma_load(
 // Cooperative global -> tile copy for shapes TMA cannot take (and as an A/B path for profiling).
 template<typename Bits, int Dims, bool Vec16>
 __device__ __forceinline__ void load_cube_ldg(uint32_t *tile, const Bits *data, const grid_geom &g, uint32_t hc, int tid) {
+    using L = input_layout<Bits, Dims>;
     const uint64_t origin = cube_origin<Dims>(g, hc);
     if constexpr (Vec16) {
         constexpr int elems_per_unit = 16 / sizeof(Bits);
@@ -164,12 +170,19 @@ __device__ __forceinline__ void load_cube_ldg(uint32_t *tile, const Bits *data, 
         for (int q = tid; q < units; q += kCubeThreads) {
             const int e = q * elems_per_unit;
             const uint4 v = ptx::ldg_stream_v4(data + origin + cube_local_offset<Dims>(g, e));
-            *reinterpret_cast<uint4 *>(tile + tile_elem<Bits>(e)) = v;
+            *reinterpret_cast<uint4 *>(tile + L::elem(e)) = v;
         }
     } else {
 #pragma unroll 8
         for (int e = tid; e < kCubeElems; e += kCubeThreads) {
-            tile_store<Bits>(tile, e, data[origin + cube_local_offset<Dims>(g, e)]);
+            const Bits v = data[origin + cube_local_offset<Dims>(g, e)];
+            const int w = L::elem(e);
+            if constexpr (sizeof(Bits) == 4) {
+                tile[w] = v;
+            } else {
+                tile[w] = static_cast<uint32_t>(v);
+                tile[w + 1] = static_cast<uint32_t>(v >> 32);
+            }
         }
     }
 }
@@ -656,6 +669,7 @@ CUresult make_input_tensor_map(CUtensorMap *map, int dtype, int dims, const void
     cuuint32_t estride[5] = {1, 1, 1, 1, 1};
     cuuint32_t rank = 0;
     CUtensorMapDataType type;
+    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
     if (dtype == 0) {
         type = CU_TENSOR_MAP_DATA_TYPE_UINT32;
         if (dims == 1) {            // [rows of 32][32]
@@ -668,11 +682,12 @@ CUresult make_input_tensor_map(CUtensorMap *map, int dtype, int dims, const void
             gdim[0] = 32; gdim[1] = n2 / 32; gdim[2] = n1;
             gstride[0] = 128; gstride[1] = n2 * 4;
             box[0] = 32; box[1] = 2; box[2] = 64;
-        } else {                    // [z][y][x]
-            rank = 3;
-            gdim[0] = n2; gdim[1] = n1; gdim[2] = n0;
-            gstride[0] = n2 * 4; gstride[1] = n1 * n2 * 4;
-            box[0] = 16; box[1] = 16; box[2] = 16;
+        } else {                    // [z][y / 2][y parity][x]; 64-byte inner rows -> SWIZZLE_64B
+            rank = 4;
+            gdim[0] = n2; gdim[1] = 2; gdim[2] = n1 / 2; gdim[3] = n0;
+            gstride[0] = n2 * 4; gstride[1] = n2 * 8; gstride[2] = n1 * n2 * 4;
+            box[0] = 16; box[1] = 1; box[2] = 8; box[3] = 16;
+            swizzle = CU_TENSOR_MAP_SWIZZLE_64B;
         }
     } else {
         type = CU_TENSOR_MAP_DATA_TYPE_UINT64;
@@ -694,7 +709,7 @@ CUresult make_input_tensor_map(CUtensorMap *map, int dtype, int dims, const void
         }
     }
     return encode(map, type, rank, const_cast<void *>(data), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
 }  // namespace ndzb

@@ -23,7 +23,11 @@ uint32_t encode_cube(const Bits *cube, Bits *out) {
     using tr = codec_traits<Bits>;
     constexpr int tile_words = tr::cube_words32 > tr::stage_words32 ? tr::cube_words32 : tr::stage_words32;
     std::vector<uint32_t> tile(tile_words, 0xdeadbeefu);
-    for (int e = 0; e < kCubeElems; ++e) tile_store<Bits>(tile.data(), e, cube[e]);
+    for (int e = 0; e < kCubeElems; ++e) {
+        const int w = input_layout<Bits, Dims>::elem(e);
+        tile[w] = static_cast<uint32_t>(cube[e]);
+        if constexpr (sizeof(Bits) == 8) tile[w + 1] = static_cast<uint32_t>(cube[e] >> 32);
+    }
 
     // phase 1: residuals (reads the input tile only)
     std::vector<Bits> res(kCubeElems);
