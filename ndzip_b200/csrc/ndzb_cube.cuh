@@ -2,7 +2,7 @@
 //
 // Everything here is __host__ __device__ and free of warp intrinsics, so the exact code the kernels
 // run can also be driven lane by lane from the CPU simulation in tests/host_sim (which checks it
-// bit for bit against the oracle without a GPU). The kernels in ndzb_compress.cu / ndzb_decompress.cu
+// bit for bit against the oracle without a GPU). The kernels in ndzb_kernels.cu
 // add the CTA-level parts: TMA / global loads, scans, the decoupled look-back, barriers.
 //
 // Work decomposition (differs from the reference's one-warp-per-chunk scheme,
@@ -11,8 +11,8 @@
 //   * computes their Lorenzo residuals straight from shared memory (reads its own run plus the
 //     1 / 2 / 5 neighbouring half-runs the stencil needs) — no in-place multi-pass transform,
 //   * bit-transposes them in registers with a 5-stage butterfly (32x32 bits per thread),
-//   * writes the 32 bit planes to a staging tile from which a warp-per-chunk pass compacts the
-//     non-zero planes directly into the output stream.
+//   * compacts the non-zero bit planes straight from registers into the cube's compressed image in
+//     shared memory (in place over the dead input tile), which is then copied out linearly.
 // float : run u == chunk u (32 values x 32 bits).
 // double: chunk c (64 values x 64 bits) == runs 2c, 2c+1; each thread transposes the high and the
 //         low words of its 32 values (two 32x32 transposes) and owns one 32-bit half of every plane.
@@ -43,17 +43,16 @@ template<> struct codec_traits<uint32_t> {
     static constexpr int chunks = 128;               // chunks per cube (cuda_codec.inl:190-194)
     static constexpr int words32_per_elem = 1;
     static constexpr int cube_words32 = 4096;        // input tile, 32-bit words
-    static constexpr int stage_words32 = 4096;       // plane staging tile (swizzled 128-byte rows)
     static constexpr int max_cube_words = 4224;      // compressed bound in Bits words (common.hh:391-392)
+    static constexpr int image_words32 = 4224;       // compressed cube image in shared memory
 };
 template<> struct codec_traits<uint64_t> {
     static constexpr int bits = 64;
     static constexpr int chunks = 64;
     static constexpr int words32_per_elem = 2;
     static constexpr int cube_words32 = 8192;
-    static constexpr int stage_row_words32 = 130;    // padded row: [plane][chunk*2 + half], +2 pad words
-    static constexpr int stage_words32 = 64 * 130;
     static constexpr int max_cube_words = 4160;
+    static constexpr int image_words32 = 2 * 4160;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -369,118 +368,88 @@ NDZB_HD uint64_t planes_of_run(const uint64_t *r, uint32_t *planes_hi, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------
-// plane staging tile
+// forward: per-thread compaction of the planes into the cube's compressed image in shared memory
 //
-// float : row c (128 bytes, swizzled like the input tile) = the 32 planes of chunk c.
-//         Writer: thread c, eight STS.128. Reader: warp lane i <-> plane i, conflict-free.
-// double: word index plane*130 + 2*chunk + half (half 0 = bits 31..0). The 130-word pitch makes both
-//         the per-thread writes (fixed plane, consecutive chunk/half across lanes) and the
-//         warp-per-chunk 64-bit reads (fixed chunk, lane <-> plane) conflict-free.
+// The compressed cube is assembled in shared memory exactly as it appears in the stream
+// ([heads][non-zero planes of chunk 0][chunk 1]...), in place over the dead input tile, and then
+// copied out linearly (coalesced). Plane i of a chunk is emitted exactly when bit B-1-i of the chunk
+// head is set (reference src/ndzip/cpu_codec.inl:514-538). `body` = word offset of the chunk's first
+// plane inside the cube (C + exclusive plane count). Three issue slots per plane (test, predicated
+// store, predicated increment) instead of a warp-per-chunk pass over all 4096 plane slots.
 
-NDZB_HD int stage_word_f32(int chunk, int plane) {
-    return tile_unit(chunk, plane >> 2) + (plane & 3);
-}
-NDZB_HD int stage_word_f64(int chunk, int plane) {  // low half; +1 = high half
-    return plane * 130 + 2 * chunk;
-}
-
-NDZB_HD void stage_planes(uint32_t *stage, int chunk, const uint32_t *planes) {
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        st_quad(stage + tile_unit(chunk, g), quad{planes[4 * g], planes[4 * g + 1], planes[4 * g + 2], planes[4 * g + 3]});
-    }
-}
-
-// `first` = this thread holds the chunk's first 32 values (run 2c) and therefore the high halves.
-NDZB_HD void stage_planes(uint32_t *stage, int chunk, bool first, const uint32_t *planes_hi,
-        const uint32_t *planes_lo) {
-    uint32_t *base = stage + 2 * chunk + (first ? 1 : 0);
+// float: image is an array of 32-bit words
+NDZB_HD void compact_planes(uint32_t *image, int chunk, uint32_t head, uint32_t body, const uint32_t *planes) {
+    image[chunk] = head;
+    uint32_t *out = image + body;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        base[i * 130] = planes_hi[i];
-        base[(i + 32) * 130] = planes_lo[i];
+        if ((head >> (31 - i)) & 1u) *out++ = planes[i];
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// forward: warp-per-chunk compaction of the staged planes into the stream
-//
-// Lane `lane` moves plane `lane` (double: planes lane and lane+32) of chunk c. Plane i is emitted
-// exactly when bit B-1-i of the chunk head is set (cpu_codec.inl:514-538); its slot inside the chunk
-// is the number of set head bits above it, so no scan is needed. `cube_out` points at the cube's
-// first stream word, `body` is the chunk's first-plane offset in words (C + exclusive plane count).
-
-NDZB_HD void emit_chunk(const uint32_t *stage, int c, int lane, uint32_t head, uint32_t body, uint32_t *cube_out) {
-    const uint32_t above = lane == 0 ? 0u : (head >> (32 - lane));  // head bits of planes 0..lane-1
-    if ((head >> (31 - lane)) & 1u) cube_out[body + popc32(above)] = stage[stage_word_f32(c, lane)];
-}
-
-NDZB_HD void emit_chunk(const uint32_t *stage, int c, int lane, uint64_t head, uint32_t body, uint64_t *cube_out) {
+// double: image is an array of 64-bit words seen as 32-bit halves (little endian: word w = halves
+// 2w, 2w+1). The thread holding the chunk's first 32 values (`first`) owns the high halves.
+NDZB_HD void compact_planes(uint32_t *image, int chunk, bool first, uint64_t head, uint32_t body,
+        const uint32_t *planes_hi, const uint32_t *planes_lo) {
     const uint32_t head_hi = static_cast<uint32_t>(head >> 32), head_lo = static_cast<uint32_t>(head);
-    const uint32_t above_hi = lane == 0 ? 0u : (head_hi >> (32 - lane));
-    const uint32_t above_lo = lane == 0 ? 0u : (head_lo >> (32 - lane));
-    if ((head_hi >> (31 - lane)) & 1u) {
-        const uint32_t *w = stage + stage_word_f64(c, lane);
-        cube_out[body + popc32(above_hi)] = (static_cast<uint64_t>(w[1]) << 32) | w[0];
-    }
-    if ((head_lo >> (31 - lane)) & 1u) {
-        const uint32_t *w = stage + stage_word_f64(c, lane + 32);
-        cube_out[body + popc32(head_hi) + popc32(above_lo)] = (static_cast<uint64_t>(w[1]) << 32) | w[0];
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// inverse: warp-per-chunk expansion of the stream into the staging tile (absent planes = 0)
-
-NDZB_HD void expand_chunk(uint32_t *stage, int c, int lane, uint32_t head, uint32_t body, const uint32_t *cube_in) {
-    const uint32_t above = lane == 0 ? 0u : (head >> (32 - lane));
-    uint32_t v = 0;
-    if ((head >> (31 - lane)) & 1u) v = cube_in[body + popc32(above)];
-    stage[stage_word_f32(c, lane)] = v;
-}
-
-NDZB_HD void expand_chunk(uint32_t *stage, int c, int lane, uint64_t head, uint32_t body, const uint64_t *cube_in) {
-    const uint32_t head_hi = static_cast<uint32_t>(head >> 32), head_lo = static_cast<uint32_t>(head);
-    const uint32_t above_hi = lane == 0 ? 0u : (head_hi >> (32 - lane));
-    const uint32_t above_lo = lane == 0 ? 0u : (head_lo >> (32 - lane));
-    uint64_t a = 0, b = 0;
-    if ((head_hi >> (31 - lane)) & 1u) a = cube_in[body + popc32(above_hi)];
-    if ((head_lo >> (31 - lane)) & 1u) b = cube_in[body + popc32(head_hi) + popc32(above_lo)];
-    uint32_t *wa = stage + stage_word_f64(c, lane);
-    uint32_t *wb = stage + stage_word_f64(c, lane + 32);
-    wa[0] = static_cast<uint32_t>(a);
-    wa[1] = static_cast<uint32_t>(a >> 32);
-    wb[0] = static_cast<uint32_t>(b);
-    wb[1] = static_cast<uint32_t>(b >> 32);
-}
-
-// ------------------------------------------------------------------------------------------------
-// inverse: residuals of run u from the staged planes (transpose is an involution,
-// reference src/test/codec_generic_test.cc:65-81), complement undone (common.hh:505-507)
-
-NDZB_HD void run_of_planes(const uint32_t *stage, int u, uint32_t *r) {
-    uint32_t a[32];
+    image[2 * chunk + (first ? 1 : 0)] = first ? head_hi : head_lo;
+    uint32_t *out = image + 2 * body + (first ? 1 : 0);
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        const quad q = ld_quad(stage + tile_unit(u, g));
-        a[31 - (4 * g + 0)] = q.x;
-        a[31 - (4 * g + 1)] = q.y;
-        a[31 - (4 * g + 2)] = q.z;
-        a[31 - (4 * g + 3)] = q.w;
+    for (int i = 0; i < 32; ++i) {
+        if ((head_hi >> (31 - i)) & 1u) {
+            *out = planes_hi[i];
+            out += 2;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if ((head_lo >> (31 - i)) & 1u) {
+            *out = planes_lo[i];
+            out += 2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// inverse: residuals of run u from the compressed image in shared memory (absent planes = 0; the
+// transpose is an involution, reference src/test/codec_generic_test.cc:65-81), complement undone
+// (common.hh:505-507)
+
+NDZB_HD void run_of_image(const uint32_t *image, uint32_t head, uint32_t body, uint32_t *r) {
+    uint32_t a[32];
+    const uint32_t *in = image + body;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        uint32_t v = 0;
+        if ((head >> (31 - i)) & 1u) v = *in++;
+        a[31 - i] = v;
     }
     transpose32(a);
 #pragma unroll
     for (int j = 0; j < 32; ++j) r[j] = complement_negative(a[31 - j]);
 }
 
-NDZB_HD void run_of_planes(const uint32_t *stage, int u, uint64_t *r) {
-    const int chunk = u >> 1;
-    const uint32_t *base = stage + 2 * chunk + ((u & 1) ? 0 : 1);
+NDZB_HD void run_of_image(const uint32_t *image, bool first, uint64_t head, uint32_t body, uint64_t *r) {
+    const uint32_t head_hi = static_cast<uint32_t>(head >> 32), head_lo = static_cast<uint32_t>(head);
     uint32_t a[32], b[32];
+    const uint32_t *in = image + 2 * body + (first ? 1 : 0);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        a[31 - i] = base[i * 130];
-        b[31 - i] = base[(i + 32) * 130];
+        uint32_t v = 0;
+        if ((head_hi >> (31 - i)) & 1u) {
+            v = *in;
+            in += 2;
+        }
+        a[31 - i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        uint32_t v = 0;
+        if ((head_lo >> (31 - i)) & 1u) {
+            v = *in;
+            in += 2;
+        }
+        b[31 - i] = v;
     }
     transpose32(a);
     transpose32(b);

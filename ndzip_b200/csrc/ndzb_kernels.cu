@@ -25,7 +25,7 @@ constexpr int kWarps = kCubeThreads / 32;
 template<typename Bits>
 struct smem_plan {
     using tr = codec_traits<Bits>;
-    static constexpr int tile_words = tr::cube_words32 > tr::stage_words32 ? tr::cube_words32 : tr::stage_words32;
+    static constexpr int tile_words = tr::cube_words32 > tr::image_words32 ? tr::cube_words32 : tr::image_words32;
     static constexpr int slot_bytes = (tile_words * 4 + 1023) / 1024 * 1024;  // SWIZZLE_128B tiles need 1024-byte alignment
 };
 
@@ -33,16 +33,12 @@ template<typename Bits>
 struct compress_aux {
     uint64_t mbar[kSlots];
     uint32_t ticket[kSlots];
-    Bits heads[codec_traits<Bits>::chunks];
-    uint32_t body_of[codec_traits<Bits>::chunks];
     uint32_t warp_total[kWarps];
     uint32_t prefix;
 };
 
 template<typename Bits>
 struct decompress_aux {
-    Bits heads[codec_traits<Bits>::chunks];
-    uint32_t body_of[codec_traits<Bits>::chunks];
     uint32_t warp_total[kWarps];
     Bits warp_sum[kWarps];
 };
@@ -206,19 +202,19 @@ __global__ void __launch_bounds__(kCubeThreads)
 
     // Work is handed out by a free-running ticket counter: ticket order == cube order, which is what
     // makes spinning on predecessors in the look-back deadlock-free (a predecessor's ticket was drawn
-    // earlier, hence by a resident CTA). Each CTA keeps kSlots tickets in flight.
+    // earlier, hence by a resident CTA). A CTA draws its next ticket only AFTER it has published the
+    // length of the cube it is working on: a ticket that is held but not being worked on would make
+    // every later cube in the grid wait for this CTA (measured: a convoy, 57 look-back polls per cube).
     if (tid == 0) {
         if constexpr (Path == load_path::tma) {
             ptx::tma_prefetch_desc(&tmap);
             for (int s = 0; s < kSlots; ++s) ptx::mbar_init(&aux.mbar[s], 1);
             ptx::fence_mbar_init();
         }
-        for (int s = 0; s < kSlots; ++s) {
-            const uint32_t t = atomicAdd(a.ticket, 1u) - a.ticket_base;
-            aux.ticket[s] = t;
-            if constexpr (Path == load_path::tma) {
-                if (t < a.count) issue_tma_load<Bits, Dims>(slots + s * slot_words, &aux.mbar[s], &tmap, a.geom, a.hc_begin + t);
-            }
+        const uint32_t t = atomicAdd(a.ticket, 1u) - a.ticket_base;
+        aux.ticket[0] = t;
+        if constexpr (Path == load_path::tma) {
+            if (t < a.count) issue_tma_load<Bits, Dims>(slots, &aux.mbar[0], &tmap, a.geom, a.hc_begin + t);
         }
     }
     __syncthreads();
@@ -229,10 +225,6 @@ __global__ void __launch_bounds__(kCubeThreads)
         if (t >= a.count) break;
         uint32_t *tile = slots + s * slot_words;
 
-        // draw the ticket this slot will serve next; its latency hides behind the cube's work
-        uint32_t next_ticket = 0;
-        if (tid == 0) next_ticket = atomicAdd(a.ticket, 1u) - a.ticket_base;
-
         if constexpr (Path == load_path::tma) {
             ptx::mbar_wait(&aux.mbar[s], (iter / kSlots) & 1u);
         } else {
@@ -240,7 +232,7 @@ __global__ void __launch_bounds__(kCubeThreads)
             __syncthreads();
         }
 
-        // ---- phase 1: residuals of run `tid`, chunk heads, plane counts -------------------------------
+        // ---- phase 1: residuals of run `tid`, chunk head, plane count ---------------------------------
         Bits r[32];
         residual_run<Bits, Dims>(tile, tid, r);
 
@@ -249,16 +241,14 @@ __global__ void __launch_bounds__(kCubeThreads)
         for (int j = 0; j < 32; ++j) head |= r[j];
         uint32_t count;
         if constexpr (sizeof(Bits) == 4) {
-            aux.heads[tid] = head;
             count = popc_bits(head);
         } else {
             head |= __shfl_xor_sync(kFullMask, head, 1);  // chunk = two adjacent runs
-            if ((tid & 1) == 0) aux.heads[tid >> 1] = head;
             count = (tid & 1) == 0 ? popc_bits(head) : 0u;
         }
         const uint32_t inclusive = warp_inclusive_sum(count, lane);
         if (lane == 31) aux.warp_total[warp] = inclusive;
-        __syncthreads();  // B1: every read of the input tile is done; heads and warp totals visible
+        __syncthreads();  // B1: every read of the input tile is done; warp totals visible
 
         uint32_t before = 0, cube_words = tr::chunks;
 #pragma unroll
@@ -267,32 +257,45 @@ __global__ void __launch_bounds__(kCubeThreads)
             cube_words += wt;
             if (w < warp) before += wt;
         }
-        if (sizeof(Bits) == 4 || (tid & 1) == 0) {
-            aux.body_of[sizeof(Bits) == 4 ? tid : tid >> 1] = tr::chunks + before + inclusive - count;
-        }
+        // word offset of this thread's chunk body inside the cube (double: both threads of the pair)
+        uint32_t body = tr::chunks + before + inclusive - count;
+        if constexpr (sizeof(Bits) == 8) body = __shfl_sync(kFullMask, body, lane & ~1);
 
-        // ---- warp 0 publishes the cube length and starts looking back ----------------------------------
+        // ---- warp 0: publish the cube length, start looking back, draw the next ticket ------------------
         uint64_t sample = 0;
+        uint32_t next_ticket = 0;
         if (warp == 0) {
             if (lane == 0) {
                 ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, t == 0 ? kStatusPrefix : kStatusAggregate, cube_words));
+                next_ticket = atomicAdd(a.ticket, 1u) - a.ticket_base;
             }
             const int64_t mine = static_cast<int64_t>(t) - 1 - lane;
             sample = mine >= 0 ? ptx::ld_relaxed_gpu(a.desc + mine) : pack_desc(a.epoch, kStatusPrefix, 0);
         }
 
-        // ---- phase 2: bit planes -> staging tile (in place over the input tile) --------------------
+        // ---- phase 2: bit planes, compacted into the cube image (in place over the input tile) --------
         if constexpr (sizeof(Bits) == 4) {
             uint32_t planes[32];
             planes_of_run(r, planes);
-            stage_planes(tile, tid, planes);
+            compact_planes(tile, tid, head, body, planes);
         } else {
             uint32_t planes_hi[32], planes_lo[32];
             planes_of_run(r, planes_hi, planes_lo);
-            stage_planes(tile, tid >> 1, (tid & 1) == 0, planes_hi, planes_lo);
+            compact_planes(tile, tid >> 1, (tid & 1) == 0, head, body, planes_hi, planes_lo);
         }
 
         if (warp == 0) {
+            if (lane == 0) {
+                // the other slot is idle (its cube left at the end of the previous iteration): prefetch
+                aux.ticket[s ^ 1] = next_ticket;
+                if constexpr (Path == load_path::tma) {
+                    if (next_ticket < a.count) {
+                        ptx::fence_proxy_async_smem();
+                        issue_tma_load<Bits, Dims>(slots + (s ^ 1) * slot_words, &aux.mbar[s ^ 1], &tmap, a.geom,
+                                a.hc_begin + next_ticket);
+                    }
+                }
+            }
             const uint32_t exclusive = t == 0 ? 0u : look_back(a.desc, t, a.epoch, lane, sample);
             if (lane == 0) {
                 const uint32_t after = exclusive + cube_words;
@@ -306,26 +309,17 @@ __global__ void __launch_bounds__(kCubeThreads)
                 }
             }
         }
-        __syncthreads();  // B2: staging tile, body offsets and the cube's stream offset are visible
+        __syncthreads();  // B2: cube image and the cube's stream offset are visible
 
-        // ---- phase 3: heads + non-zero planes -> final stream position -------------------------------
-        Bits *cube_out = out_cubes + aux.prefix;
-        if (tid < tr::chunks) cube_out[tid] = aux.heads[tid];
+        // ---- phase 3: coalesced copy of the cube image to its final stream position --------------------
+        {
+            constexpr int w32 = sizeof(Bits) / 4;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(out_cubes + aux.prefix);
+            const int n = static_cast<int>(cube_words) * w32;
 #pragma unroll 4
-        for (int c = warp; c < tr::chunks; c += kWarps) {
-            emit_chunk(tile, c, lane, aux.heads[c], aux.body_of[c], cube_out);
+            for (int w = tid; w < n; w += kCubeThreads) dst[w] = tile[w];
         }
         __syncthreads();  // B3: the slot is free
-
-        if (tid == 0) {
-            aux.ticket[s] = next_ticket;
-            if constexpr (Path == load_path::tma) {
-                if (next_ticket < a.count) {
-                    ptx::fence_proxy_async_smem();
-                    issue_tma_load<Bits, Dims>(tile, &aux.mbar[s], &tmap, a.geom, a.hc_begin + next_ticket);
-                }
-            }
-        }
     }
 }
 
@@ -365,14 +359,31 @@ __global__ void __launch_bounds__(kCubeThreads) decompress_kernel(const decompre
     for (uint32_t t = blockIdx.x; t < a.count; t += gridDim.x) {
         const uint32_t hc = a.hc_begin + t;
         const uint32_t begin = hc ? __ldg(a.offsets + hc - 1) : 0u;  // reference src/ndzip/common.hh:350-358
+        const uint32_t end = __ldg(a.offsets + hc);
         const Bits *cube_in = stream_cubes + begin;
 
-        // ---- heads -> where each chunk's planes start ---------------------------------------------
-        uint32_t count = 0;
-        if (tid < tr::chunks) {
-            const Bits head = cube_in[tid];
-            aux.heads[tid] = head;
+        // ---- coalesced copy of the compressed cube into shared memory ----------------------------------
+        {
+            constexpr int w32 = sizeof(Bits) / 4;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(cube_in);
+            uint32_t len = end - begin;
+            if (len > static_cast<uint32_t>(tr::max_cube_words)) len = tr::max_cube_words;  // corrupt header: stay in bounds
+            const int n = static_cast<int>(len) * w32;
+#pragma unroll 4
+            for (int w = tid; w < n; w += kCubeThreads) tile[w] = __ldg(src + w);
+        }
+        __syncthreads();
+
+        // ---- chunk heads -> where each chunk's planes start ------------------------------------------------
+        Bits head;
+        uint32_t count;
+        if constexpr (sizeof(Bits) == 4) {
+            head = tile[tid];
             count = popc_bits(head);
+        } else {
+            const int c = tid >> 1;
+            head = (static_cast<uint64_t>(tile[2 * c + 1]) << 32) | tile[2 * c];
+            count = (tid & 1) == 0 ? popc_bits(head) : 0u;
         }
         const uint32_t inclusive = warp_inclusive_sum(count, lane);
         if (lane == 31) aux.warp_total[warp] = inclusive;
@@ -382,19 +393,16 @@ __global__ void __launch_bounds__(kCubeThreads) decompress_kernel(const decompre
         for (int w = 0; w < kWarps; ++w) {
             if (w < warp) before += aux.warp_total[w];
         }
-        if (tid < tr::chunks) aux.body_of[tid] = tr::chunks + before + inclusive - count;
-        __syncthreads();
-
-        // ---- warp-per-chunk expansion: stream -> plane staging tile ------------------------------
-#pragma unroll 4
-        for (int c = warp; c < tr::chunks; c += kWarps) {
-            expand_chunk(tile, c, lane, aux.heads[c], aux.body_of[c], cube_in);
-        }
-        __syncthreads();
+        uint32_t body = tr::chunks + before + inclusive - count;
+        if constexpr (sizeof(Bits) == 8) body = __shfl_sync(kFullMask, body, lane & ~1);
 
         // ---- per-thread: planes -> residuals of run `tid`; x-direction prefix sums ------------------
         Bits r[32];
-        run_of_planes(tile, tid, r);
+        if constexpr (sizeof(Bits) == 4) {
+            run_of_image(tile, head, body, r);
+        } else {
+            run_of_image(tile, (tid & 1) == 0, head, body, r);
+        }
         if constexpr (Dims == 3) {
 #pragma unroll
             for (int i = 1; i < 16; ++i) {
@@ -426,8 +434,8 @@ __global__ void __launch_bounds__(kCubeThreads) decompress_kernel(const decompre
                 for (int j = 0; j < 32; ++j) r[j] += left;
             }
         }
-        // the double staging tile is not thread-private: everyone must have read before anyone writes
-        if constexpr (sizeof(Bits) == 8) __syncthreads();
+        // the value tile aliases the compressed image: everyone must have read before anyone writes
+        __syncthreads();
         store_run(tile, tid, r);
         __syncthreads();
 
@@ -545,7 +553,7 @@ size_t decompress_smem(int dtype) { return dtype == 0 ? decompress_smem_bytes<ui
 // =====================================================================================================
 
 uint32_t compress_ticket_overdraw(uint32_t grid) {
-    return grid * kSlots;  // every CTA draws kSlots tickets up front and one more per cube it processes
+    return grid;  // every CTA draws one ticket up front and one more per cube it processes
 }
 
 cudaError_t configure_kernels(kernel_config &cfg) {

@@ -21,7 +21,7 @@ uint32_t popc_bits(Bits v) {
 template<typename Bits, int Dims>
 uint32_t encode_cube(const Bits *cube, Bits *out) {
     using tr = codec_traits<Bits>;
-    constexpr int tile_words = tr::cube_words32 > tr::stage_words32 ? tr::cube_words32 : tr::stage_words32;
+    constexpr int tile_words = tr::cube_words32 > tr::image_words32 ? tr::cube_words32 : tr::image_words32;
     std::vector<uint32_t> tile(tile_words, 0xdeadbeefu);
     for (int e = 0; e < kCubeElems; ++e) {
         const int w = input_layout<Bits, Dims>::elem(e);
@@ -29,53 +29,61 @@ uint32_t encode_cube(const Bits *cube, Bits *out) {
         if constexpr (sizeof(Bits) == 8) tile[w + 1] = static_cast<uint32_t>(cube[e] >> 32);
     }
 
-    // phase 1: residuals (reads the input tile only)
+    // phase 1: residuals (reads the input tile only), heads, plane counts
     std::vector<Bits> res(kCubeElems);
     for (int u = 0; u < kCubeThreads; ++u) residual_run<Bits, Dims>(tile.data(), u, &res[32 * u]);
-
-    // phase 2: planes -> staging tile (aliases the input tile, as in the kernel)
     Bits heads[tr::chunks];
+    for (int c = 0; c < tr::chunks; ++c) heads[c] = 0;
+    for (int e = 0; e < kCubeElems; ++e) heads[e / tr::bits] |= res[e];
+    uint32_t body[tr::chunks];
+    uint32_t total = tr::chunks;
+    for (int c = 0; c < tr::chunks; ++c) {
+        body[c] = total;
+        total += popc_bits(heads[c]);
+    }
+
+    // phase 2: planes, compacted into the cube image (aliases the input tile, as in the kernel)
     if constexpr (sizeof(Bits) == 4) {
         for (int u = 0; u < kCubeThreads; ++u) {
             uint32_t planes[32];
-            heads[u] = planes_of_run(&res[32 * u], planes);
-            stage_planes(tile.data(), u, planes);
+            planes_of_run(&res[32 * u], planes);
+            compact_planes(tile.data(), u, heads[u], body[u], planes);
         }
     } else {
-        for (int c = 0; c < tr::chunks; ++c) heads[c] = 0;
         for (int u = 0; u < kCubeThreads; ++u) {
             uint32_t ph[32], pl[32];
-            heads[u >> 1] |= planes_of_run(&res[32 * u], ph, pl);
-            stage_planes(tile.data(), u >> 1, (u & 1) == 0, ph, pl);
+            planes_of_run(&res[32 * u], ph, pl);
+            compact_planes(tile.data(), u >> 1, (u & 1) == 0, heads[u >> 1], body[u >> 1], ph, pl);
         }
     }
 
-    // phase 3: heads + warp-per-chunk compaction
-    uint32_t body = tr::chunks;
-    for (int c = 0; c < tr::chunks; ++c) {
-        out[c] = heads[c];
-        for (int lane = 0; lane < 32; ++lane) emit_chunk(tile.data(), c, lane, heads[c], body, out);
-        body += popc_bits(heads[c]);
-    }
-    return body;
+    // phase 3: linear copy-out
+    memcpy(out, tile.data(), static_cast<size_t>(total) * sizeof(Bits));
+    return total;
 }
 
 template<typename Bits, int Dims>
 uint32_t decode_cube(const Bits *in, Bits *cube) {
     using tr = codec_traits<Bits>;
-    constexpr int tile_words = tr::cube_words32 > tr::stage_words32 ? tr::cube_words32 : tr::stage_words32;
+    constexpr int tile_words = tr::cube_words32 > tr::image_words32 ? tr::cube_words32 : tr::image_words32;
     std::vector<uint32_t> stage(tile_words, 0xdeadbeefu);
-    uint32_t body = tr::chunks;
+    uint32_t body[tr::chunks];
+    uint32_t total = tr::chunks;
     for (int c = 0; c < tr::chunks; ++c) {
-        for (int lane = 0; lane < 32; ++lane) expand_chunk(stage.data(), c, lane, in[c], body, in);
-        body += popc_bits(in[c]);
+        body[c] = total;
+        total += popc_bits(in[c]);
     }
+    memcpy(stage.data(), in, static_cast<size_t>(total) * sizeof(Bits));  // coalesced copy-in
 
-    // per-thread: planes -> residual run, x-direction prefix inside the run
+    // per-thread: image -> residual run, x-direction prefix inside the run
     std::vector<Bits> res(kCubeElems);
     for (int u = 0; u < kCubeThreads; ++u) {
         Bits *r = &res[32 * u];
-        run_of_planes(stage.data(), u, r);
+        if constexpr (sizeof(Bits) == 4) {
+            run_of_image(stage.data(), in[u], body[u], r);
+        } else {
+            run_of_image(stage.data(), (u & 1) == 0, in[u >> 1], body[u >> 1], r);
+        }
         if constexpr (Dims == 3) {
             for (int i = 1; i < 16; ++i) { r[i] += r[i - 1]; r[16 + i] += r[16 + i - 1]; }
         } else {
@@ -96,7 +104,7 @@ uint32_t decode_cube(const Bits *in, Bits *cube) {
             for (int j = 0; j < 32; ++j) res[32 * u + j] += left;
         }
     }
-    // the value tile aliases the plane staging tile (every thread rewrites only what it read)
+    // the value tile aliases the compressed image (barrier in the kernel: all reads before any write)
     for (int u = 0; u < kCubeThreads; ++u) store_run(stage.data(), u, &res[32 * u]);
 
     // remaining axes: column passes in shared memory
@@ -115,7 +123,7 @@ uint32_t decode_cube(const Bits *in, Bits *cube) {
         for (int yx = 0; yx < 256; ++yx) column_pass(yx, 256, 16);
     }
     for (int e = 0; e < kCubeElems; ++e) cube[e] = rotr1(tile_load<Bits>(stage.data(), e));
-    return body;
+    return total;
 }
 
 template<typename Bits>
