@@ -19,7 +19,7 @@ namespace ndzb {
 namespace {
 
 constexpr uint32_t kFullMask = 0xffffffffu;
-constexpr int kSlots = 2;   // input tiles in flight per CTA (TMA double buffering)
+constexpr int kSlots = 3;   // cube tiles per CTA: being copied out / being encoded / being loaded by TMA
 constexpr int kWarps = kCubeThreads / 32;
 
 template<typename Bits>
@@ -34,7 +34,7 @@ struct compress_aux {
     uint64_t mbar[kSlots];
     uint32_t ticket[kSlots];
     uint32_t warp_total[kWarps];
-    uint32_t prefix;
+    uint32_t prefix[2];
 };
 
 template<typename Bits>
@@ -87,28 +87,55 @@ __device__ __forceinline__ uint32_t desc_status(uint64_t d, uint32_t epoch) {
     return (hi >> 2) == epoch ? (hi & 3u) : 0u;
 }
 
-// Exclusive offset of cube t (> 0) = sum of the lengths of cubes 0..t-1. Executed by one full warp;
-// lane l inspects predecessor idx-l. `first` is lane's pre-loaded sample of desc[t-1-lane].
-__device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, uint32_t epoch, int lane, uint64_t first) {
+// Exclusive offset of cube t (> 0) = sum of the lengths of cubes 0..t-1. Executed by one full warp.
+// Each step inspects a window of 32*kLookBackDepth predecessors (lane l looks at idx-l, idx-32-l, ...):
+// at ~200 cubes/us and ~1 us L2 latency the nearest cube whose inclusive prefix is already published is
+// typically ~100 cubes back, so a 32-wide window needs several dependent round trips (measured: 2-3).
+constexpr int kLookBackDepth = 2;
+
+__device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, uint32_t epoch, int lane) {
     uint32_t exclusive = 0;
     int64_t idx = static_cast<int64_t>(t) - 1;
-    uint64_t d = first;
-    bool have_sample = true;
     while (true) {
-        const int64_t mine = idx - lane;
-        uint32_t status;
+        uint64_t d[kLookBackDepth];
+        uint32_t status[kLookBackDepth];
         while (true) {
-            if (!have_sample) d = mine >= 0 ? ptx::ld_relaxed_gpu(desc + mine) : pack_desc(epoch, kStatusPrefix, 0);
-            have_sample = false;
-            status = desc_status(d, epoch);
-            if (!__any_sync(kFullMask, status == 0)) break;
-            __nanosleep(32);
+            bool pending = false;
+#pragma unroll
+            for (int k = 0; k < kLookBackDepth; ++k) {
+                const int64_t mine = idx - 32 * k - lane;
+                d[k] = mine >= 0 ? ptx::ld_relaxed_gpu(desc + mine) : pack_desc(epoch, kStatusPrefix, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < kLookBackDepth; ++k) {
+                status[k] = desc_status(d[k], epoch);
+                pending |= status[k] == 0;
+            }
+            // only predecessors nearer than the nearest published prefix have to be valid
+            uint32_t need_wait = 0;
+            bool found = false;
+#pragma unroll
+            for (int k = 0; k < kLookBackDepth; ++k) {
+                const uint32_t invalid = __ballot_sync(kFullMask, status[k] == 0);
+                const uint32_t prefix = __ballot_sync(kFullMask, status[k] == kStatusPrefix);
+                if (!found) {
+                    const uint32_t nearer = prefix ? ((1u << (__ffs(prefix) - 1)) - 1u) : 0xffffffffu;
+                    need_wait |= invalid & nearer;
+                    found = prefix != 0;
+                }
+            }
+            (void) pending;
+            if (need_wait == 0) break;
+            __nanosleep(20);
         }
-        const uint32_t prefix_lanes = __ballot_sync(kFullMask, status == kStatusPrefix);
-        const int nearest = prefix_lanes ? __ffs(prefix_lanes) - 1 : 32;
-        exclusive += __reduce_add_sync(kFullMask, lane <= nearest ? static_cast<uint32_t>(d) : 0u);
-        if (prefix_lanes) return exclusive;
-        idx -= 32;
+#pragma unroll
+        for (int k = 0; k < kLookBackDepth; ++k) {
+            const uint32_t prefix_lanes = __ballot_sync(kFullMask, status[k] == kStatusPrefix);
+            const int nearest = prefix_lanes ? __ffs(prefix_lanes) - 1 : 32;
+            exclusive += __reduce_add_sync(kFullMask, lane <= nearest ? static_cast<uint32_t>(d[k]) : 0u);
+            if (prefix_lanes) return exclusive;
+        }
+        idx -= 32 * kLookBackDepth;
     }
 }
 
@@ -202,9 +229,14 @@ __global__ void __launch_bounds__(kCubeThreads)
 
     // Work is handed out by a free-running ticket counter: ticket order == cube order, which is what
     // makes spinning on predecessors in the look-back deadlock-free (a predecessor's ticket was drawn
-    // earlier, hence by a resident CTA). A CTA draws its next ticket only AFTER it has published the
-    // length of the cube it is working on: a ticket that is held but not being worked on would make
-    // every later cube in the grid wait for this CTA (measured: a convoy, 57 look-back polls per cube).
+    // earlier, hence by a resident CTA).
+    //
+    // Software pipeline over three tiles (profiles/r1_compress_notes.md has the measurements behind it):
+    //   iteration i:  encode cube t_i (publish its length early)  |  TMA is loading cube t_{i+1}
+    //                 then look back + copy out cube t_{i-1}
+    // A cube's length is therefore always published BEFORE this CTA may block in a look-back, and every
+    // look-back gets a full iteration of slack. (Blocking first made the time from drawing a ticket to
+    // publishing its length depend on other cubes' look-backs: a convoy, 57 polls per cube.)
     if (tid == 0) {
         if constexpr (Path == load_path::tma) {
             ptx::tma_prefetch_desc(&tmap);
@@ -219,107 +251,116 @@ __global__ void __launch_bounds__(kCubeThreads)
     }
     __syncthreads();
 
+    constexpr uint32_t kNone = 0xffffffffu;
+    uint32_t prev_t = kNone, prev_words = 0;
+    int prev_slot = 0;
+
     for (uint32_t iter = 0;; ++iter) {
         const int s = iter % kSlots;
-        const uint32_t t = aux.ticket[s];  // cube index within the launch's range
-        if (t >= a.count) break;
+        const uint32_t t = aux.ticket[s];  // cube index within the launch's range (CTA-uniform)
+        const bool have = t < a.count;
         uint32_t *tile = slots + s * slot_words;
+        uint32_t cube_words = 0;
 
-        if constexpr (Path == load_path::tma) {
-            ptx::mbar_wait(&aux.mbar[s], (iter / kSlots) & 1u);
-        } else {
-            load_cube_ldg<Bits, Dims, Path == load_path::vec16>(tile, data, a.geom, a.hc_begin + t, tid);
-            __syncthreads();
-        }
+        if (have) {
+            if constexpr (Path == load_path::tma) {
+                ptx::mbar_wait(&aux.mbar[s], (iter / kSlots) & 1u);
+            } else {
+                load_cube_ldg<Bits, Dims, Path == load_path::vec16>(tile, data, a.geom, a.hc_begin + t, tid);
+                __syncthreads();
+            }
 
-        // ---- phase 1: residuals of run `tid`, chunk head, plane count ---------------------------------
-        Bits r[32];
-        residual_run<Bits, Dims>(tile, tid, r);
+            // ---- phase 1: residuals of run `tid`, chunk head, plane count -----------------------------
+            Bits r[32];
+            residual_run<Bits, Dims>(tile, tid, r);
 
-        Bits head = 0;
+            Bits head = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) head |= r[j];
-        uint32_t count;
-        if constexpr (sizeof(Bits) == 4) {
-            count = popc_bits(head);
-        } else {
-            head |= __shfl_xor_sync(kFullMask, head, 1);  // chunk = two adjacent runs
-            count = (tid & 1) == 0 ? popc_bits(head) : 0u;
-        }
-        const uint32_t inclusive = warp_inclusive_sum(count, lane);
-        if (lane == 31) aux.warp_total[warp] = inclusive;
-        __syncthreads();  // B1: every read of the input tile is done; warp totals visible
+            for (int j = 0; j < 32; ++j) head |= r[j];
+            uint32_t count;
+            if constexpr (sizeof(Bits) == 4) {
+                count = popc_bits(head);
+            } else {
+                head |= __shfl_xor_sync(kFullMask, head, 1);  // chunk = two adjacent runs
+                count = (tid & 1) == 0 ? popc_bits(head) : 0u;
+            }
+            const uint32_t inclusive = warp_inclusive_sum(count, lane);
+            if (lane == 31) aux.warp_total[warp] = inclusive;
+            __syncthreads();  // B1: every read of the input tile is done; warp totals visible
 
-        uint32_t before = 0, cube_words = tr::chunks;
+            uint32_t before = 0;
+            cube_words = tr::chunks;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const uint32_t wt = aux.warp_total[w];
-            cube_words += wt;
-            if (w < warp) before += wt;
-        }
-        // word offset of this thread's chunk body inside the cube (double: both threads of the pair)
-        uint32_t body = tr::chunks + before + inclusive - count;
-        if constexpr (sizeof(Bits) == 8) body = __shfl_sync(kFullMask, body, lane & ~1);
+            for (int w = 0; w < kWarps; ++w) {
+                const uint32_t wt = aux.warp_total[w];
+                cube_words += wt;
+                if (w < warp) before += wt;
+            }
+            // word offset of this thread's chunk body inside the cube (double: both threads of the pair)
+            uint32_t body = tr::chunks + before + inclusive - count;
+            if constexpr (sizeof(Bits) == 8) body = __shfl_sync(kFullMask, body, lane & ~1);
 
-        // ---- warp 0: publish the cube length, start looking back, draw the next ticket ------------------
-        uint64_t sample = 0;
-        uint32_t next_ticket = 0;
-        if (warp == 0) {
-            if (lane == 0) {
+            // ---- publish the cube length, draw the next ticket (its latency hides behind phase 2) ------
+            uint32_t next_ticket = 0;
+            if (tid == 0) {
                 ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, t == 0 ? kStatusPrefix : kStatusAggregate, cube_words));
                 next_ticket = atomicAdd(a.ticket, 1u) - a.ticket_base;
             }
-            const int64_t mine = static_cast<int64_t>(t) - 1 - lane;
-            sample = mine >= 0 ? ptx::ld_relaxed_gpu(a.desc + mine) : pack_desc(a.epoch, kStatusPrefix, 0);
-        }
 
-        // ---- phase 2: bit planes, compacted into the cube image (in place over the input tile) --------
-        if constexpr (sizeof(Bits) == 4) {
-            uint32_t planes[32];
-            planes_of_run(r, planes);
-            compact_planes(tile, tid, head, body, planes);
-        } else {
-            uint32_t planes_hi[32], planes_lo[32];
-            planes_of_run(r, planes_hi, planes_lo);
-            compact_planes(tile, tid >> 1, (tid & 1) == 0, head, body, planes_hi, planes_lo);
-        }
+            // ---- phase 2: bit planes, compacted into the cube image (in place over the input tile) ----
+            if constexpr (sizeof(Bits) == 4) {
+                uint32_t planes[32];
+                planes_of_run(r, planes);
+                compact_planes(tile, tid, head, body, planes);
+            } else {
+                uint32_t planes_hi[32], planes_lo[32];
+                planes_of_run(r, planes_hi, planes_lo);
+                compact_planes(tile, tid >> 1, (tid & 1) == 0, head, body, planes_hi, planes_lo);
+            }
 
-        if (warp == 0) {
-            if (lane == 0) {
-                // the other slot is idle (its cube left at the end of the previous iteration): prefetch
-                aux.ticket[s ^ 1] = next_ticket;
+            if (tid == 0) {
+                // tile (iter+1)%kSlots was copied out during the previous iteration: prefetch into it
+                const int sn = (iter + 1) % kSlots;
+                aux.ticket[sn] = next_ticket;
                 if constexpr (Path == load_path::tma) {
                     if (next_ticket < a.count) {
                         ptx::fence_proxy_async_smem();
-                        issue_tma_load<Bits, Dims>(slots + (s ^ 1) * slot_words, &aux.mbar[s ^ 1], &tmap, a.geom,
-                                a.hc_begin + next_ticket);
+                        issue_tma_load<Bits, Dims>(slots + sn * slot_words, &aux.mbar[sn], &tmap, a.geom, a.hc_begin + next_ticket);
                     }
                 }
             }
-            const uint32_t exclusive = t == 0 ? 0u : look_back(a.desc, t, a.epoch, lane, sample);
+        }
+
+        // ---- the previous cube: look back (it has had a whole iteration to become cheap) -------------
+        if (prev_t != kNone && warp == 0) {
+            const uint32_t exclusive = prev_t == 0 ? 0u : look_back(a.desc, prev_t, a.epoch, lane);
             if (lane == 0) {
-                const uint32_t after = exclusive + cube_words;
-                if (t != 0) ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, kStatusPrefix, after));
-                aux.prefix = exclusive;
-                a.out_offsets[t] = after;  // "offset_after", reference src/ndzip/common.hh:342-347
-                if (t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452
-                if (t == a.count - 1) {
+                const uint32_t after = exclusive + prev_words;
+                if (prev_t != 0) ptx::st_relaxed_gpu(a.desc + prev_t, pack_desc(a.epoch, kStatusPrefix, after));
+                aux.prefix[iter & 1] = exclusive;
+                a.out_offsets[prev_t] = after;  // "offset_after", reference src/ndzip/common.hh:342-347
+                if (prev_t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452
+                if (prev_t == a.count - 1) {
                     *a.total_words = after;
                     if (a.length_out) *a.length_out = a.length_add + after;  // cuda_codec.inl:507-511
                 }
             }
         }
-        __syncthreads();  // B2: cube image and the cube's stream offset are visible
+        __syncthreads();  // B2: this iteration's cube image and the previous cube's stream offset are visible
 
-        // ---- phase 3: coalesced copy of the cube image to its final stream position --------------------
-        {
+        // ---- coalesced copy of the previous cube's image to its final stream position ---------------
+        if (prev_t != kNone) {
             constexpr int w32 = sizeof(Bits) / 4;
-            uint32_t *dst = reinterpret_cast<uint32_t *>(out_cubes + aux.prefix);
-            const int n = static_cast<int>(cube_words) * w32;
+            const uint32_t *src = slots + prev_slot * slot_words;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(out_cubes + aux.prefix[iter & 1]);
+            const int n = static_cast<int>(prev_words) * w32;
 #pragma unroll 4
-            for (int w = tid; w < n; w += kCubeThreads) dst[w] = tile[w];
+            for (int w = tid; w < n; w += kCubeThreads) dst[w] = src[w];
         }
-        __syncthreads();  // B3: the slot is free
+        if (!have) break;
+        prev_t = t;
+        prev_words = cube_words;
+        prev_slot = s;
     }
 }
 
