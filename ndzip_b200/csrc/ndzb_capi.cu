@@ -47,6 +47,8 @@ grid_geom make_geom(int dims, const uint32_t *size) {
         g.cubes[3 - dims + d] = size[d] / side;
         g.num_cubes *= size[d] / side;  // reference src/ndzip/common.hh:395-402
     }
+    g.div_x = make_fastdiv(g.cubes[2]);
+    g.div_y = make_fastdiv(g.cubes[1]);
     return g;
 }
 

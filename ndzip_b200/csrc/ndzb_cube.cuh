@@ -497,27 +497,69 @@ template<> NDZB_HD void tile_store<uint64_t>(uint32_t *tile, int e, uint64_t v) 
 // ------------------------------------------------------------------------------------------------
 // geometry shared by kernels and host code
 
+// Exact unsigned division by a launch-invariant divisor without the ~20-instruction hardware
+// sequence (Granlund-Montgomery round-up method): n / d = (t + ((n - t) >> sh1)) >> sh2, t = mulhi(mul, n).
+struct fastdiv {
+    uint32_t mul, sh1, sh2;
+};
+
+NDZB_HD fastdiv make_fastdiv(uint32_t d) {
+    fastdiv f{1, 0, 0};
+    if (d <= 1) return f;
+    uint32_t log2_ceil = 0;
+    while ((1ull << log2_ceil) < d) ++log2_ceil;
+    f.mul = static_cast<uint32_t>((((1ull << log2_ceil) - d) << 32) / d + 1);
+    f.sh1 = 1;
+    f.sh2 = log2_ceil - 1;
+    return f;
+}
+
+NDZB_HD uint32_t fast_divide(uint32_t n, const fastdiv &f) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t t = __umulhi(f.mul, n);
+#else
+    const uint32_t t = static_cast<uint32_t>((static_cast<uint64_t>(f.mul) * n) >> 32);
+#endif
+    return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+
 struct grid_geom {
     // element extents, slowest first, padded with 1 in front so index 2 is always the fastest
     uint32_t n[3];
     uint32_t cubes[3];       // whole cubes per dimension (padded with 1)
     uint32_t num_cubes;
+    fastdiv div_x, div_y;    // division by cubes[2] / cubes[1]
 };
 
-// Linear element offset of the first element of hypercube `hc` (row-major cube order, slowest
-// dimension first; reference src/ndzip/common.hh:414-433, 570-579).
+// hc -> cube coordinates (cube units). Cubes are numbered row-major over cube coordinates, slowest
+// dimension first (reference src/ndzip/common.hh:414-433, 570-579).
+template<int Dims>
+NDZB_HD void cube_coords(const grid_geom &g, uint32_t hc, uint32_t &cz, uint32_t &cy, uint32_t &cx) {
+    cz = cy = 0;
+    if constexpr (Dims == 1) {
+        cx = hc;
+    } else if constexpr (Dims == 2) {
+        cy = fast_divide(hc, g.div_x);
+        cx = hc - cy * g.cubes[2];
+    } else {
+        const uint32_t t = fast_divide(hc, g.div_x);
+        cx = hc - t * g.cubes[2];
+        cz = fast_divide(t, g.div_y);
+        cy = t - cz * g.cubes[1];
+    }
+}
+
+// Linear element offset of the first element of hypercube `hc`.
 template<int Dims>
 NDZB_HD uint64_t cube_origin(const grid_geom &g, uint32_t hc) {
     constexpr uint32_t side = side_of<Dims>::value;
+    uint32_t cz, cy, cx;
+    cube_coords<Dims>(g, hc, cz, cy, cx);
     if constexpr (Dims == 1) {
-        return static_cast<uint64_t>(hc) * side;
+        return static_cast<uint64_t>(cx) * side;
     } else if constexpr (Dims == 2) {
-        const uint32_t cy = hc / g.cubes[2], cx = hc % g.cubes[2];
         return (static_cast<uint64_t>(cy) * side) * g.n[2] + static_cast<uint64_t>(cx) * side;
     } else {
-        const uint32_t cx = hc % g.cubes[2];
-        const uint32_t t = hc / g.cubes[2];
-        const uint32_t cy = t % g.cubes[1], cz = t / g.cubes[1];
         return ((static_cast<uint64_t>(cz) * side) * g.n[1] + static_cast<uint64_t>(cy) * side) * g.n[2]
                 + static_cast<uint64_t>(cx) * side;
     }

@@ -42,14 +42,20 @@ struct decompress_aux {
     uint32_t warp_total[kWarps];
     Bits warp_sum[kWarps];
 };
+constexpr int kDecodeBuffers = 2;  // compressed cube being decoded / next one streaming in (cp.async)
 
 template<typename Bits>
 constexpr size_t compress_smem_bytes() {
     return static_cast<size_t>(kSlots) * smem_plan<Bits>::slot_bytes + sizeof(compress_aux<Bits>);
 }
 template<typename Bits>
+struct decode_plan {
+    // compressed image (+ up to 3 words of alignment shift) or value tile, whichever is larger
+    static constexpr int buffer_bytes = ((codec_traits<Bits>::image_words32 + 8) * 4 + 1023) / 1024 * 1024;
+};
+template<typename Bits>
 constexpr size_t decompress_smem_bytes() {
-    return static_cast<size_t>(smem_plan<Bits>::slot_bytes) + sizeof(decompress_aux<Bits>);
+    return static_cast<size_t>(kDecodeBuffers) * decode_plan<Bits>::buffer_bytes + sizeof(decompress_aux<Bits>);
 }
 
 __device__ __forceinline__ uint32_t popc_bits(uint32_t v) { return __popc(v); }
@@ -93,29 +99,35 @@ __device__ __forceinline__ uint32_t desc_status(uint64_t d, uint32_t epoch) {
 // typically ~100 cubes back, so a 32-wide window needs several dependent round trips (measured: 2-3).
 constexpr int kLookBackDepth = 2;
 
-__device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, uint32_t epoch, int lane) {
+struct look_back_sample {
+    uint64_t d[kLookBackDepth];
+};
+
+// Loads the descriptors of the window ending at predecessor `idx` (lane l: idx-l, idx-32-l, ...).
+__device__ __forceinline__ look_back_sample look_back_load(const uint64_t *desc, int64_t idx, uint32_t epoch, int lane) {
+    look_back_sample s;
+#pragma unroll
+    for (int k = 0; k < kLookBackDepth; ++k) {
+        const int64_t mine = idx - 32 * k - lane;
+        s.d[k] = mine >= 0 ? ptx::ld_relaxed_gpu(desc + mine) : pack_desc(epoch, kStatusPrefix, 0);
+    }
+    return s;
+}
+
+// `first` is a sample of the first window taken earlier (its L2 latency hidden behind other work).
+__device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, uint32_t epoch, int lane, look_back_sample first) {
     uint32_t exclusive = 0;
     int64_t idx = static_cast<int64_t>(t) - 1;
+    look_back_sample s = first;
     while (true) {
-        uint64_t d[kLookBackDepth];
         uint32_t status[kLookBackDepth];
         while (true) {
-            bool pending = false;
-#pragma unroll
-            for (int k = 0; k < kLookBackDepth; ++k) {
-                const int64_t mine = idx - 32 * k - lane;
-                d[k] = mine >= 0 ? ptx::ld_relaxed_gpu(desc + mine) : pack_desc(epoch, kStatusPrefix, 0);
-            }
-#pragma unroll
-            for (int k = 0; k < kLookBackDepth; ++k) {
-                status[k] = desc_status(d[k], epoch);
-                pending |= status[k] == 0;
-            }
             // only predecessors nearer than the nearest published prefix have to be valid
             uint32_t need_wait = 0;
             bool found = false;
 #pragma unroll
             for (int k = 0; k < kLookBackDepth; ++k) {
+                status[k] = desc_status(s.d[k], epoch);
                 const uint32_t invalid = __ballot_sync(kFullMask, status[k] == 0);
                 const uint32_t prefix = __ballot_sync(kFullMask, status[k] == kStatusPrefix);
                 if (!found) {
@@ -124,18 +136,19 @@ __device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, 
                     found = prefix != 0;
                 }
             }
-            (void) pending;
             if (need_wait == 0) break;
             __nanosleep(20);
+            s = look_back_load(desc, idx, epoch, lane);
         }
 #pragma unroll
         for (int k = 0; k < kLookBackDepth; ++k) {
             const uint32_t prefix_lanes = __ballot_sync(kFullMask, status[k] == kStatusPrefix);
             const int nearest = prefix_lanes ? __ffs(prefix_lanes) - 1 : 32;
-            exclusive += __reduce_add_sync(kFullMask, lane <= nearest ? static_cast<uint32_t>(d[k]) : 0u);
+            exclusive += __reduce_add_sync(kFullMask, lane <= nearest ? static_cast<uint32_t>(s.d[k]) : 0u);
             if (prefix_lanes) return exclusive;
         }
         idx -= 32 * kLookBackDepth;
+        s = look_back_load(desc, idx, epoch, lane);
     }
 }
 
@@ -146,36 +159,26 @@ __device__ __forceinline__ void issue_tma_load(
         uint32_t *slot, uint64_t *bar, const CUtensorMap *map, const grid_geom &g, uint32_t hc) {
     constexpr uint32_t bytes = codec_traits<Bits>::cube_words32 * 4;
     ptx::mbar_arrive_expect_tx(bar, bytes);
-    if constexpr (sizeof(Bits) == 4) {
-        if constexpr (Dims == 1) {
-            ptx::tma_load_2d(slot, map, bar, 0, static_cast<int>(hc * 128));
-        } else if constexpr (Dims == 2) {
-            const uint32_t cy = hc / g.cubes[2], cx = hc % g.cubes[2];
-            ptx::tma_load_3d(slot, map, bar, 0, static_cast<int>(cx * 2), static_cast<int>(cy * 64));
-        } else {
-            // two 8 KiB regions: even-y rows, odd-y rows (view [z][y/2][y parity][x], SWIZZLE_64B)
-            const uint32_t cx = hc % g.cubes[2], t = hc / g.cubes[2];
-            const uint32_t cy = t % g.cubes[1], cz = t / g.cubes[1];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                ptx::tma_load_4d(slot + h * input_layout<uint32_t, 3>::region_words, map, bar, static_cast<int>(cx * 16), h,
-                        static_cast<int>(cy * 8), static_cast<int>(cz * 16));
-            }
-        }
+    uint32_t ucz, ucy, ucx;
+    cube_coords<Dims>(g, hc, ucz, ucy, ucx);
+    const int cz = static_cast<int>(ucz), cy = static_cast<int>(ucy), cx = static_cast<int>(ucx);
+    if constexpr (sizeof(Bits) == 4 && Dims == 1) {
+        ptx::tma_load_2d(slot, map, bar, 0, cx * 128);
+    } else if constexpr (sizeof(Bits) == 4 && Dims == 2) {
+        ptx::tma_load_3d(slot, map, bar, 0, cx * 2, cy * 64);
     } else {
-        // two 16 KiB regions: region h holds the h-th 16-value half of every run
+        // two regions: float 3D = even-y / odd-y rows (view [z][y/2][y parity][x], SWIZZLE_64B);
+        //              double   = first / second 16-value half of every run
+        constexpr int region_words = input_layout<Bits, Dims>::region_words;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            uint32_t *dst = slot + (h << 12);
+            uint32_t *dst = slot + h * region_words;
             if constexpr (Dims == 1) {
-                ptx::tma_load_3d(dst, map, bar, 0, h, static_cast<int>(hc * 128));
+                ptx::tma_load_3d(dst, map, bar, 0, h, cx * 128);
             } else if constexpr (Dims == 2) {
-                const uint32_t cy = hc / g.cubes[2], cx = hc % g.cubes[2];
-                ptx::tma_load_4d(dst, map, bar, 0, h, static_cast<int>(cx * 2), static_cast<int>(cy * 64));
+                ptx::tma_load_4d(dst, map, bar, 0, h, cx * 2, cy * 64);
             } else {
-                const uint32_t cx = hc % g.cubes[2], t = hc / g.cubes[2];
-                const uint32_t cy = t % g.cubes[1], cz = t / g.cubes[1];
-                ptx::tma_load_4d(dst, map, bar, static_cast<int>(cx * 16), h, static_cast<int>(cy * 8), static_cast<int>(cz * 16));
+                ptx::tma_load_4d(dst, map, bar, cx * 16, h, cy * 8, cz * 16);
             }
         }
     }
@@ -262,6 +265,9 @@ __global__ void __launch_bounds__(kCubeThreads)
         uint32_t *tile = slots + s * slot_words;
         uint32_t cube_words = 0;
 
+        look_back_sample sample{};
+        bool sampled = false;
+
         if (have) {
             if constexpr (Path == load_path::tma) {
                 ptx::mbar_wait(&aux.mbar[s], (iter / kSlots) & 1u);
@@ -300,10 +306,19 @@ __global__ void __launch_bounds__(kCubeThreads)
             uint32_t body = tr::chunks + before + inclusive - count;
             if constexpr (sizeof(Bits) == 8) body = __shfl_sync(kFullMask, body, lane & ~1);
 
-            // ---- publish the cube length, draw the next ticket (its latency hides behind phase 2) ------
+            // ---- publish the cube length; sample the previous cube's look-back window; draw the next ticket.
+            // All three are L2 round trips whose latency hides behind phase 2. The serial bookkeeping is
+            // spread over two warps (warp 0: look-back, warp 1: ticket + TMA) to keep the barrier short.
             uint32_t next_ticket = 0;
-            if (tid == 0) {
-                ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, t == 0 ? kStatusPrefix : kStatusAggregate, cube_words));
+            if (warp == 0) {
+                if (lane == 0) {
+                    ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, t == 0 ? kStatusPrefix : kStatusAggregate, cube_words));
+                }
+                if (prev_t != kNone && prev_t != 0) {
+                    sample = look_back_load(a.desc, static_cast<int64_t>(prev_t) - 1, a.epoch, lane);
+                    sampled = true;
+                }
+            } else if (tid == 32) {
                 next_ticket = atomicAdd(a.ticket, 1u) - a.ticket_base;
             }
 
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(kCubeThreads)
                 compact_planes(tile, tid >> 1, (tid & 1) == 0, head, body, planes_hi, planes_lo);
             }
 
-            if (tid == 0) {
+            if (tid == 32) {
                 // tile (iter+1)%kSlots was copied out during the previous iteration: prefetch into it
                 const int sn = (iter + 1) % kSlots;
                 aux.ticket[sn] = next_ticket;
@@ -333,7 +348,8 @@ __global__ void __launch_bounds__(kCubeThreads)
 
         // ---- the previous cube: look back (it has had a whole iteration to become cheap) -------------
         if (prev_t != kNone && warp == 0) {
-            const uint32_t exclusive = prev_t == 0 ? 0u : look_back(a.desc, prev_t, a.epoch, lane);
+            if (!sampled && prev_t != 0) sample = look_back_load(a.desc, static_cast<int64_t>(prev_t) - 1, a.epoch, lane);
+            const uint32_t exclusive = prev_t == 0 ? 0u : look_back(a.desc, prev_t, a.epoch, lane, sample);
             if (lane == 0) {
                 const uint32_t after = exclusive + prev_words;
                 if (prev_t != 0) ptx::st_relaxed_gpu(a.desc + prev_t, pack_desc(a.epoch, kStatusPrefix, after));
@@ -386,44 +402,81 @@ __device__ __forceinline__ void column_prefix(uint32_t *tile, int first, int str
     }
 }
 
-template<typename Bits, int Dims, bool Vec16>
-__global__ void __launch_bounds__(kCubeThreads) decompress_kernel(const decompress_launch a) {
+// Streams the compressed cube [begin, end) (stream words) into `buf` with cp.async so that image
+// word w lands at buf[shift + w], shift = the cube's misalignment to 16 bytes: the body moves in
+// 16-byte copies, the ragged head and tail in 4-byte copies (never touches bytes outside the cube).
+template<typename Bits>
+__device__ __forceinline__ void stream_in_cube(uint32_t *buf, const Bits *stream_cubes, uint32_t begin, uint32_t end, int tid) {
     using tr = codec_traits<Bits>;
+    constexpr int w32 = sizeof(Bits) / 4;
+    uint32_t len = end - begin;
+    if (len > static_cast<uint32_t>(tr::max_cube_words)) len = tr::max_cube_words;  // corrupt header: stay inside the buffer
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(stream_cubes + begin);
+    const int n = static_cast<int>(len) * w32;
+    const int shift = static_cast<int>((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+    const int head = (4 - shift) & 3;            // words before the first 16-byte boundary
+    const int body_groups = n > head ? (n - head) >> 2 : 0;
+    const int tail_begin = head + (body_groups << 2);
+    for (int g = tid; g < body_groups; g += kCubeThreads) {
+        ptx::cp_async_16(buf + shift + head + 4 * g, src + head + 4 * g);
+    }
+    if (tid < head && tid < n) ptx::cp_async_4(buf + shift + tid, src + tid);
+    if (tid >= 32 && tid - 32 < n - tail_begin && tail_begin >= head) ptx::cp_async_4(buf + shift + tail_begin + (tid - 32), src + tail_begin + (tid - 32));
+}
+
+template<typename Bits, int Dims, bool Vec16>
+__global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 5 : 3) decompress_kernel(const decompress_launch a) {
+    using tr = codec_traits<Bits>;
+    constexpr int buf_words = decode_plan<Bits>::buffer_bytes / 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint32_t *tile = reinterpret_cast<uint32_t *>(smem_raw);
-    auto &aux = *reinterpret_cast<decompress_aux<Bits> *>(smem_raw + smem_plan<Bits>::slot_bytes);
+    uint32_t *bufs = reinterpret_cast<uint32_t *>(smem_raw);
+    auto &aux = *reinterpret_cast<decompress_aux<Bits> *>(smem_raw + kDecodeBuffers * decode_plan<Bits>::buffer_bytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const Bits *stream_cubes = static_cast<const Bits *>(a.stream_cubes);
     Bits *data = static_cast<Bits *>(a.data);
 
-    for (uint32_t t = blockIdx.x; t < a.count; t += gridDim.x) {
-        const uint32_t hc = a.hc_begin + t;
-        const uint32_t begin = hc ? __ldg(a.offsets + hc - 1) : 0u;  // reference src/ndzip/common.hh:350-358
-        const uint32_t end = __ldg(a.offsets + hc);
-        const Bits *cube_in = stream_cubes + begin;
-
-        // ---- coalesced copy of the compressed cube into shared memory ----------------------------------
-        {
-            constexpr int w32 = sizeof(Bits) / 4;
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(cube_in);
-            uint32_t len = end - begin;
-            if (len > static_cast<uint32_t>(tr::max_cube_words)) len = tr::max_cube_words;  // corrupt header: stay in bounds
-            const int n = static_cast<int>(len) * w32;
-#pragma unroll 4
-            for (int w = tid; w < n; w += kCubeThreads) tile[w] = __ldg(src + w);
+    // Cubes are independent: static round-robin over the grid. The stream offsets of a cube are read
+    // two iterations ahead and its compressed words are streamed in one iteration ahead.
+    auto offsets_of = [&](uint32_t t, uint32_t &begin, uint32_t &end) {
+        begin = end = 0;
+        if (t < a.count) {
+            const uint32_t hc = a.hc_begin + t;
+            begin = hc ? __ldg(a.offsets + hc - 1) : 0u;  // reference src/ndzip/common.hh:350-358
+            end = __ldg(a.offsets + hc);
         }
+    };
+    uint32_t cur_begin, cur_end, next_begin, next_end;
+    offsets_of(blockIdx.x, cur_begin, cur_end);
+    offsets_of(blockIdx.x + gridDim.x, next_begin, next_end);
+    if (blockIdx.x < a.count) stream_in_cube<Bits>(bufs, stream_cubes, cur_begin, cur_end, tid);
+    ptx::cp_async_commit();
+
+    for (uint32_t k = 0, t = blockIdx.x; t < a.count; ++k, t += gridDim.x) {
+        const uint32_t hc = a.hc_begin + t;
+        uint32_t *tile = bufs + (k & 1) * buf_words;
+        // prefetch: next cube's words into the other buffer (free since the end of the previous iteration),
+        // the cube after that's offsets into registers
+        if (t + gridDim.x < a.count) stream_in_cube<Bits>(bufs + ((k + 1) & 1) * buf_words, stream_cubes, next_begin, next_end, tid);
+        ptx::cp_async_commit();
+        const uint32_t begin = cur_begin;
+        cur_begin = next_begin;
+        cur_end = next_end;
+        offsets_of(t + 2 * gridDim.x, next_begin, next_end);
+
+        ptx::cp_async_wait<1>();  // everything but the newest group (the prefetch) has landed
         __syncthreads();
+        const uint32_t *image = tile + ((reinterpret_cast<uintptr_t>(stream_cubes + begin) >> 2) & 3);
 
         // ---- chunk heads -> where each chunk's planes start ------------------------------------------------
         Bits head;
         uint32_t count;
         if constexpr (sizeof(Bits) == 4) {
-            head = tile[tid];
+            head = image[tid];
             count = popc_bits(head);
         } else {
             const int c = tid >> 1;
-            head = (static_cast<uint64_t>(tile[2 * c + 1]) << 32) | tile[2 * c];
+            head = (static_cast<uint64_t>(image[2 * c + 1]) << 32) | image[2 * c];
             count = (tid & 1) == 0 ? popc_bits(head) : 0u;
         }
         const uint32_t inclusive = warp_inclusive_sum(count, lane);
@@ -440,9 +493,9 @@ __global__ void __launch_bounds__(kCubeThreads) decompress_kernel(const decompre
         // ---- per-thread: planes -> residuals of run `tid`; x-direction prefix sums ------------------
         Bits r[32];
         if constexpr (sizeof(Bits) == 4) {
-            run_of_image(tile, head, body, r);
+            run_of_image(image, head, body, r);
         } else {
-            run_of_image(tile, (tid & 1) == 0, head, body, r);
+            run_of_image(image, (tid & 1) == 0, head, body, r);
         }
         if constexpr (Dims == 3) {
 #pragma unroll

@@ -153,6 +153,8 @@ grid_geom make_geom(int dims, const uint32_t *size) {
         g.cubes[3 - dims + d] = size[d] / side;
         g.num_cubes *= size[d] / side;
     }
+    g.div_x = make_fastdiv(g.cubes[2]);
+    g.div_y = make_fastdiv(g.cubes[1]);
     return g;
 }
 
