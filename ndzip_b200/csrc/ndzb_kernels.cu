@@ -234,13 +234,17 @@ __global__ void __launch_bounds__(kCubeThreads)
     // makes spinning on predecessors in the look-back deadlock-free (a predecessor's ticket was drawn
     // earlier, hence by a resident CTA).
     //
-    // Software pipeline over three tiles (profiles/r1_compress_notes.md has the measurements behind it):
-    //   iteration i:  encode cube t_i (publish its length early)  |  TMA is loading cube t_{i+1}
+    // Software pipeline over three tiles (profiles/README.md has the measurements behind each choice):
+    //   iteration i:  encode cube t_i and publish its length   |  TMA is loading cube t_{i+1}
     //                 then look back + copy out cube t_{i-1}
-    // A cube's length is therefore always published BEFORE this CTA may block in a look-back, and every
-    // look-back gets a full iteration of slack. (Blocking first made the time from drawing a ticket to
-    // publishing its length depend on other cubes' look-backs: a convoy, 57 polls per cube.)
-    if (tid == 0) {
+    // * A cube's length is always published BEFORE this CTA may wait in a look-back, and every look-back
+    //   gets a full iteration of slack. (Waiting first made the time from drawing a ticket to publishing
+    //   its length depend on other cubes' look-backs: a convoy, 57 polls per cube.)
+    // * Thread 32 owns tickets and TMA: the ticket for iteration i+1 is drawn at the top of iteration i
+    //   and its TMA is issued right after barrier B1; warp 0 owns the look-back. Letting every warp
+    //   resolve the look-back itself (no second barrier) was measured and is slower (redundant polls).
+    constexpr int kTicketThread = 32;
+    if (tid == kTicketThread) {
         if constexpr (Path == load_path::tma) {
             ptx::tma_prefetch_desc(&tmap);
             for (int s = 0; s < kSlots; ++s) ptx::mbar_init(&aux.mbar[s], 1);
@@ -264,11 +268,13 @@ __global__ void __launch_bounds__(kCubeThreads)
         const bool have = t < a.count;
         uint32_t *tile = slots + s * slot_words;
         uint32_t cube_words = 0;
-
         look_back_sample sample{};
         bool sampled = false;
 
         if (have) {
+            uint32_t next_ticket = 0;
+            if (tid == kTicketThread) next_ticket = atomicAdd(a.ticket, 1u) - a.ticket_base;
+
             if constexpr (Path == load_path::tma) {
                 ptx::mbar_wait(&aux.mbar[s], (iter / kSlots) & 1u);
             } else {
@@ -292,7 +298,8 @@ __global__ void __launch_bounds__(kCubeThreads)
             }
             const uint32_t inclusive = warp_inclusive_sum(count, lane);
             if (lane == 31) aux.warp_total[warp] = inclusive;
-            __syncthreads();  // B1: every read of the input tile is done; warp totals visible
+            if (tid == kTicketThread) aux.ticket[(iter + 1) % kSlots] = next_ticket;
+            __syncthreads();  // B1: reads of the input tile done; warp totals and the next ticket visible
 
             uint32_t before = 0;
             cube_words = tr::chunks;
@@ -306,10 +313,8 @@ __global__ void __launch_bounds__(kCubeThreads)
             uint32_t body = tr::chunks + before + inclusive - count;
             if constexpr (sizeof(Bits) == 8) body = __shfl_sync(kFullMask, body, lane & ~1);
 
-            // ---- publish the cube length; sample the previous cube's look-back window; draw the next ticket.
-            // All three are L2 round trips whose latency hides behind phase 2. The serial bookkeeping is
-            // spread over two warps (warp 0: look-back, warp 1: ticket + TMA) to keep the barrier short.
-            uint32_t next_ticket = 0;
+            // ---- publish the cube length + sample the previous cube's look-back window (warp 0);
+            //      prefetch the next cube (thread 32). All are L2 round trips hidden behind phase 2.
             if (warp == 0) {
                 if (lane == 0) {
                     ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, t == 0 ? kStatusPrefix : kStatusAggregate, cube_words));
@@ -318,8 +323,14 @@ __global__ void __launch_bounds__(kCubeThreads)
                     sample = look_back_load(a.desc, static_cast<int64_t>(prev_t) - 1, a.epoch, lane);
                     sampled = true;
                 }
-            } else if (tid == 32) {
-                next_ticket = atomicAdd(a.ticket, 1u) - a.ticket_base;
+            }
+            if constexpr (Path == load_path::tma) {
+                if (tid == kTicketThread && next_ticket < a.count) {
+                    // tile (iter+1)%kSlots was copied out during the previous iteration, i.e. before B1
+                    const int sn = (iter + 1) % kSlots;
+                    ptx::fence_proxy_async_smem();
+                    issue_tma_load<Bits, Dims>(slots + sn * slot_words, &aux.mbar[sn], &tmap, a.geom, a.hc_begin + next_ticket);
+                }
             }
 
             // ---- phase 2: bit planes, compacted into the cube image (in place over the input tile) ----
@@ -331,18 +342,6 @@ __global__ void __launch_bounds__(kCubeThreads)
                 uint32_t planes_hi[32], planes_lo[32];
                 planes_of_run(r, planes_hi, planes_lo);
                 compact_planes(tile, tid >> 1, (tid & 1) == 0, head, body, planes_hi, planes_lo);
-            }
-
-            if (tid == 32) {
-                // tile (iter+1)%kSlots was copied out during the previous iteration: prefetch into it
-                const int sn = (iter + 1) % kSlots;
-                aux.ticket[sn] = next_ticket;
-                if constexpr (Path == load_path::tma) {
-                    if (next_ticket < a.count) {
-                        ptx::fence_proxy_async_smem();
-                        issue_tma_load<Bits, Dims>(slots + sn * slot_words, &aux.mbar[sn], &tmap, a.geom, a.hc_begin + next_ticket);
-                    }
-                }
             }
         }
 
