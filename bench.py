@@ -407,17 +407,23 @@ def main():
     if world > 1 and args.gather:
         cube_words = int(n_words - hdr_words)
         layout = nzd.exchange_layout(dtype, global_shape, torch.tensor([cube_words], device=dev))
-        sync_all()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        exchange()
-        out = nzd.gather_global_stream(layout, d_stream, d_header_global, root=0)
-        g1.record()
-        sync_all()
-        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        gather_info = {"ms": float(gt.item()), "global_stream_bytes": int(layout.global_stream_words * itemsize)}
+        out = nzd.gather_global_stream(layout, d_stream, d_header_global, root=0)  # warm-up: NCCL p2p connections
         del out
+        times = []
+        for _ in range(3):
+            sync_all()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            exchange()
+            out = nzd.gather_global_stream(layout, d_stream, d_header_global, root=0)
+            g1.record()
+            sync_all()
+            gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+            times.append(float(gt.item()))
+            del out
+        gather_info = {"ms": min(times), "global_stream_bytes": int(layout.global_stream_words * itemsize),
+                       "note": "offset exchange + NCCL send/recv of every rank's cube segment to rank 0 (includes allocating/zeroing the global buffer)"}
 
     # ---- e2e: host-pointer offloader API, pinned buffers, copies inside the timed region (rank-local)
     e2e = None

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <vector>
 
 using namespace ndzb;
 
@@ -107,6 +108,10 @@ struct ndzb_ctx {
     size_t d_out_bytes = 0;
     uint32_t *d_length = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // pipelined offload: copy-in / copy-out streams, per-chunk events, pinned per-chunk totals
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done, ev_k0, ev_k1;
+    uint32_t *h_totals = nullptr;  // pinned
 };
 
 namespace {
@@ -144,7 +149,8 @@ load_path choose_path(const ndzb_ctx *ctx, const void *data, const grid_geom &g)
 
 // Enqueue the compression of cubes [hc_begin, hc_begin + count) (count > 0).
 int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g, uint32_t hc_begin, uint32_t count,
-        void *out_cubes, uint32_t *out_offsets, uint32_t *pad_word, uint32_t *length_out, uint32_t length_add) {
+        void *out_cubes, uint32_t *out_offsets, uint32_t *pad_word, uint32_t *length_out, uint32_t length_add,
+        const uint32_t *base_words = nullptr) {
     if (int rc = ensure_descriptors(ctx, count)) return rc;
     const load_path path = choose_path(ctx, d_data, g);
     CUtensorMap map{};
@@ -164,6 +170,7 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
     a.out_cubes = out_cubes;
     a.out_offsets = out_offsets;
     a.pad_word = pad_word;
+    a.base_words = base_words;
     a.total_words = ctx->d_counters + 1;
     a.length_out = length_out;
     a.length_add = length_add;
@@ -203,6 +210,178 @@ int enqueue_decompress_range(ndzb_ctx *ctx, const void *stream_cubes, const uint
     if (e != cudaSuccess) return cuda_fail(e, "decompress_kernel launch");
     ctx->last_launches += 1;
     return NDZB_OK;
+}
+
+// ---- pipelined host<->device path -------------------------------------------------
+// The grid is cut into slabs of whole cube rows along dimension 0. H2D of slab c+1, the kernels of slab c
+// and D2H of slab c-1 run on three streams, so the call is bounded by max(H2D, D2H) over PCIe instead of
+// their sum. Used for border-free extents above a size threshold; everything else takes the simple path.
+constexpr int kMaxChunks = 64;
+constexpr size_t kChunkBytes = size_t{32} << 20;
+constexpr size_t kPipelineMinBytes = size_t{16} << 20;
+
+size_t pipeline_min_bytes() {
+    if (const char *env = getenv("NDZB_PIPELINE_MIN_BYTES")) return strtoull(env, nullptr, 10);
+    return kPipelineMinBytes;
+}
+
+struct chunk_plan {
+    int chunks = 0;
+    uint32_t rows_per_chunk = 0;   // cube rows (along dimension 0) per chunk
+    uint32_t cube_rows = 0;
+    uint32_t cubes_per_row = 0;
+    uint64_t elems_per_cube_row = 0;
+};
+
+chunk_plan plan_chunks(int dims, const uint32_t *size, const grid_geom &g, size_t elem_bytes) {
+    chunk_plan p;
+    p.cube_rows = size[0] / side_for(dims);
+    if (p.cube_rows == 0) return p;
+    p.cubes_per_row = g.num_cubes / p.cube_rows;
+    p.elems_per_cube_row = static_cast<uint64_t>(side_for(dims));
+    for (int d = 1; d < dims; ++d) p.elems_per_cube_row *= size[d];
+    const uint64_t row_bytes = p.elems_per_cube_row * elem_bytes;
+    uint64_t chunk_bytes = kChunkBytes;
+    if (const char *env = getenv("NDZB_CHUNK_BYTES")) chunk_bytes = strtoull(env, nullptr, 10);  // tests / tuning
+    uint64_t rows = chunk_bytes / (row_bytes ? row_bytes : 1);
+    if (rows == 0) rows = 1;
+    uint64_t chunks = (p.cube_rows + rows - 1) / rows;
+    if (chunks > kMaxChunks) {
+        rows = (p.cube_rows + kMaxChunks - 1) / kMaxChunks;
+        chunks = (p.cube_rows + rows - 1) / rows;
+    }
+    p.rows_per_chunk = static_cast<uint32_t>(rows);
+    p.chunks = static_cast<int>(chunks);
+    return p;
+}
+
+int ensure_pipeline(ndzb_ctx *ctx, int chunks) {
+    if (!ctx->s_in) NDZB_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    if (!ctx->s_out) NDZB_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    if (!ctx->h_totals) NDZB_CUDA(cudaHostAlloc(&ctx->h_totals, kMaxChunks * sizeof(uint32_t), cudaHostAllocDefault));
+    while (static_cast<int>(ctx->ev_in.size()) < chunks) {
+        cudaEvent_t a, b, c, d;
+        NDZB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        NDZB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        NDZB_CUDA(cudaEventCreate(&c));
+        NDZB_CUDA(cudaEventCreate(&d));
+        ctx->ev_in.push_back(a);
+        ctx->ev_done.push_back(b);
+        ctx->ev_k0.push_back(c);
+        ctx->ev_k1.push_back(d);
+    }
+    return NDZB_OK;
+}
+
+int sum_kernel_time(ndzb_ctx *ctx, int chunks, uint64_t *kernel_ns) {
+    if (!kernel_ns) return NDZB_OK;
+    double total_ms = 0;
+    for (int c = 0; c < chunks; ++c) {
+        float ms = 0;
+        NDZB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_k0[c], ctx->ev_k1[c]));
+        total_ms += ms;
+    }
+    *kernel_ns = static_cast<uint64_t>(total_ms * 1e6);
+    return NDZB_OK;
+}
+
+int pipelined_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uint32_t *size, void *h_stream,
+        uint32_t *length_words, uint64_t *kernel_ns, const grid_geom &g, const chunk_plan &plan) {
+    const size_t wb = word_bytes(ctx->dtype);
+    const uint32_t H = g.num_cubes;
+    const uint32_t hdr = header_words(ctx->dtype, H);
+    const uint64_t n_elems = num_elements(dims, size);
+    if (int rc = ensure_pipeline(ctx, plan.chunks)) return rc;
+    if (int rc = ensure_descriptors(ctx, H)) return rc;  // before anything is enqueued: growing synchronises
+    char *d_in = static_cast<char *>(ctx->d_in);
+    char *d_out = static_cast<char *>(ctx->d_out);
+    const char *h_in = static_cast<const char *>(h_data);
+    char *h_out = static_cast<char *>(h_stream);
+    uint32_t *offsets = static_cast<uint32_t *>(ctx->d_out);
+    void *cubes = d_out + static_cast<size_t>(hdr) * wb;
+    uint32_t *pad = (ctx->dtype == NDZB_F64 && (H & 1u)) ? offsets + H : nullptr;
+
+    // whatever the caller enqueued on the context's stream comes first
+    NDZB_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    NDZB_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->ev_begin, 0));
+    NDZB_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_begin, 0));
+
+    for (int c = 0; c < plan.chunks; ++c) {
+        const uint32_t row0 = c * plan.rows_per_chunk;
+        const uint32_t row1 = (c + 1 == plan.chunks) ? plan.cube_rows : row0 + plan.rows_per_chunk;
+        const uint64_t e0 = row0 * plan.elems_per_cube_row;
+        const uint64_t e1 = (c + 1 == plan.chunks) ? n_elems : row1 * plan.elems_per_cube_row;
+        NDZB_CUDA(cudaMemcpyAsync(d_in + e0 * wb, h_in + e0 * wb, (e1 - e0) * wb, cudaMemcpyHostToDevice, ctx->s_in));
+        NDZB_CUDA(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+        NDZB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0));
+        NDZB_CUDA(cudaEventRecord(ctx->ev_k0[c], ctx->stream));
+        const uint32_t hb = row0 * plan.cubes_per_row, he = row1 * plan.cubes_per_row;
+        if (int rc = enqueue_compress_range(ctx, ctx->d_in, g, hb, he - hb, cubes, offsets + hb, c == 0 ? pad : nullptr,
+                    c + 1 == plan.chunks ? ctx->d_length : nullptr, hdr, c ? ctx->d_counters + 1 : nullptr)) {
+            return rc;
+        }
+        NDZB_CUDA(cudaEventRecord(ctx->ev_k1[c], ctx->stream));
+        NDZB_CUDA(cudaMemcpyAsync(ctx->h_totals + c, ctx->d_counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        NDZB_CUDA(cudaEventRecord(ctx->ev_done[c], ctx->stream));
+    }
+    // drain: as soon as a chunk's total is known on the host, its cubes go back on the copy-out stream
+    uint32_t prev = 0;
+    for (int c = 0; c < plan.chunks; ++c) {
+        NDZB_CUDA(cudaEventSynchronize(ctx->ev_done[c]));
+        const uint32_t tot = ctx->h_totals[c];
+        const size_t off = (static_cast<size_t>(hdr) + prev) * wb;
+        if (tot > prev) NDZB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, static_cast<size_t>(tot - prev) * wb, cudaMemcpyDeviceToHost, ctx->s_out));
+        prev = tot;
+    }
+    NDZB_CUDA(cudaMemcpyAsync(h_out, d_out, static_cast<size_t>(hdr) * wb, cudaMemcpyDeviceToHost, ctx->s_out));
+    NDZB_CUDA(cudaStreamSynchronize(ctx->s_out));
+    NDZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *length_words = hdr + prev;
+    return sum_kernel_time(ctx, plan.chunks, kernel_ns);
+}
+
+int pipelined_decompress(ndzb_ctx *ctx, const void *h_stream, void *h_data, int dims, const uint32_t *size,
+        uint64_t *kernel_ns, const grid_geom &g, const chunk_plan &plan) {
+    const size_t wb = word_bytes(ctx->dtype);
+    const uint32_t H = g.num_cubes;
+    const uint32_t hdr = header_words(ctx->dtype, H);
+    const uint64_t n_elems = num_elements(dims, size);
+    if (int rc = ensure_pipeline(ctx, plan.chunks)) return rc;
+    char *d_stream = static_cast<char *>(ctx->d_out);
+    char *d_data = static_cast<char *>(ctx->d_in);
+    const char *h_in = static_cast<const char *>(h_stream);
+    const uint32_t *h_offsets = static_cast<const uint32_t *>(h_stream);
+    char *h_out = static_cast<char *>(h_data);
+
+    NDZB_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    NDZB_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->ev_begin, 0));
+    NDZB_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_begin, 0));
+    NDZB_CUDA(cudaMemcpyAsync(d_stream, h_in, static_cast<size_t>(hdr) * wb, cudaMemcpyHostToDevice, ctx->s_in));
+
+    for (int c = 0; c < plan.chunks; ++c) {
+        const uint32_t row0 = c * plan.rows_per_chunk;
+        const uint32_t row1 = (c + 1 == plan.chunks) ? plan.cube_rows : row0 + plan.rows_per_chunk;
+        const uint32_t hb = row0 * plan.cubes_per_row, he = row1 * plan.cubes_per_row;
+        const size_t w0 = static_cast<size_t>(hdr) + (hb ? h_offsets[hb - 1] : 0u);
+        const size_t w1 = static_cast<size_t>(hdr) + h_offsets[he - 1];
+        NDZB_CUDA(cudaMemcpyAsync(d_stream + w0 * wb, h_in + w0 * wb, (w1 - w0) * wb, cudaMemcpyHostToDevice, ctx->s_in));
+        NDZB_CUDA(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+        NDZB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0));
+        NDZB_CUDA(cudaEventRecord(ctx->ev_k0[c], ctx->stream));
+        if (int rc = enqueue_decompress_range(ctx, d_stream + static_cast<size_t>(hdr) * wb, reinterpret_cast<const uint32_t *>(d_stream),
+                    ctx->d_in, g, hb, he - hb)) {
+            return rc;
+        }
+        NDZB_CUDA(cudaEventRecord(ctx->ev_k1[c], ctx->stream));
+        NDZB_CUDA(cudaEventRecord(ctx->ev_done[c], ctx->stream));
+        NDZB_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[c], 0));
+        const uint64_t e0 = row0 * plan.elems_per_cube_row;
+        const uint64_t e1 = (c + 1 == plan.chunks) ? n_elems : row1 * plan.elems_per_cube_row;
+        NDZB_CUDA(cudaMemcpyAsync(h_out + e0 * wb, d_data + e0 * wb, (e1 - e0) * wb, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    NDZB_CUDA(cudaStreamSynchronize(ctx->s_out));
+    NDZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return sum_kernel_time(ctx, plan.chunks, kernel_ns);
 }
 
 int check_call(const ndzb_ctx *ctx, int dims, const uint32_t *size) {
@@ -264,6 +443,12 @@ void ndzb_ctx_destroy(ndzb_ctx *ctx) {
     if (ctx->d_length) cudaFree(ctx->d_length);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    for (auto *v : {&ctx->ev_in, &ctx->ev_done, &ctx->ev_k0, &ctx->ev_k1}) {
+        for (cudaEvent_t e : *v) cudaEventDestroy(e);
+    }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     delete ctx;
 }
 
@@ -378,6 +563,18 @@ int ndzb_offload_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uin
     if (int rc = ensure_buffer(&ctx->d_in, &ctx->d_in_bytes, in_bytes ? in_bytes : 16)) return rc;
     if (int rc = ensure_buffer(&ctx->d_out, &ctx->d_out_bytes, bound_bytes ? bound_bytes : 16)) return rc;
     if (!ctx->d_length) NDZB_CUDA(cudaMalloc(&ctx->d_length, sizeof(uint32_t)));
+    {
+        const grid_geom g = make_geom(dims, size);
+        if (g.num_cubes > 0 && make_border(dims, size).count == 0 && in_bytes >= pipeline_min_bytes() && !getenv("NDZB_NO_PIPELINE")) {
+            const chunk_plan plan = plan_chunks(dims, size, g, wb);
+            if (plan.chunks > 1) {
+                ctx->last_launches = 0;
+                const int rc = pipelined_compress(ctx, h_data, dims, size, h_stream, length_words, kernel_ns, g, plan);
+                ctx->last_launches = static_cast<uint32_t>(plan.chunks);
+                return rc;
+            }
+        }
+    }
     if (in_bytes) NDZB_CUDA(cudaMemcpyAsync(ctx->d_in, h_data, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     NDZB_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
     if (int rc = ndzb_compress(ctx, ctx->d_in, dims, size, ctx->d_out, ctx->d_length)) return rc;
@@ -405,6 +602,21 @@ int ndzb_offload_decompress(ndzb_ctx *ctx, const void *h_stream, uint32_t length
     if (out_bytes && (!h_data || !h_stream)) return NDZB_ERR_INVALID_ARGUMENT;
     if (int rc = ensure_buffer(&ctx->d_out, &ctx->d_out_bytes, in_bytes ? in_bytes : 16)) return rc;
     if (int rc = ensure_buffer(&ctx->d_in, &ctx->d_in_bytes, out_bytes ? out_bytes : 16)) return rc;
+    {
+        const grid_geom g = make_geom(dims, size);
+        if (g.num_cubes > 0 && make_border(dims, size).count == 0 && out_bytes >= pipeline_min_bytes() && !getenv("NDZB_NO_PIPELINE")) {
+            const chunk_plan plan = plan_chunks(dims, size, g, wb);
+            if (plan.chunks > 1) {
+                const int rc = pipelined_decompress(ctx, h_stream, h_data, dims, size, kernel_ns, g, plan);
+                ctx->last_launches = static_cast<uint32_t>(plan.chunks);
+                if (rc == NDZB_OK && consumed_words) {
+                    const uint32_t H = g.num_cubes;
+                    *consumed_words = header_words(ctx->dtype, H) + static_cast<const uint32_t *>(h_stream)[H - 1];
+                }
+                return rc;
+            }
+        }
+    }
     if (in_bytes) NDZB_CUDA(cudaMemcpyAsync(ctx->d_out, h_stream, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     NDZB_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
     if (int rc = ndzb_decompress(ctx, ctx->d_out, ctx->d_in, dims, size)) return rc;

@@ -104,18 +104,19 @@ struct look_back_sample {
 };
 
 // Loads the descriptors of the window ending at predecessor `idx` (lane l: idx-l, idx-32-l, ...).
-__device__ __forceinline__ look_back_sample look_back_load(const uint64_t *desc, int64_t idx, uint32_t epoch, int lane) {
+// Positions before cube 0 read as a published prefix equal to the launch's base offset.
+__device__ __forceinline__ look_back_sample look_back_load(const uint64_t *desc, int64_t idx, uint32_t epoch, int lane, uint32_t base) {
     look_back_sample s;
 #pragma unroll
     for (int k = 0; k < kLookBackDepth; ++k) {
         const int64_t mine = idx - 32 * k - lane;
-        s.d[k] = mine >= 0 ? ptx::ld_relaxed_gpu(desc + mine) : pack_desc(epoch, kStatusPrefix, 0);
+        s.d[k] = mine >= 0 ? ptx::ld_relaxed_gpu(desc + mine) : pack_desc(epoch, kStatusPrefix, base);
     }
     return s;
 }
 
 // `first` is a sample of the first window taken earlier (its L2 latency hidden behind other work).
-__device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, uint32_t epoch, int lane, look_back_sample first) {
+__device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, uint32_t epoch, int lane, look_back_sample first, uint32_t base) {
     uint32_t exclusive = 0;
     int64_t idx = static_cast<int64_t>(t) - 1;
     look_back_sample s = first;
@@ -138,7 +139,7 @@ __device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, 
             }
             if (need_wait == 0) break;
             __nanosleep(20);
-            s = look_back_load(desc, idx, epoch, lane);
+            s = look_back_load(desc, idx, epoch, lane, base);
         }
 #pragma unroll
         for (int k = 0; k < kLookBackDepth; ++k) {
@@ -148,7 +149,7 @@ __device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, 
             if (prefix_lanes) return exclusive;
         }
         idx -= 32 * kLookBackDepth;
-        s = look_back_load(desc, idx, epoch, lane);
+        s = look_back_load(desc, idx, epoch, lane, base);
     }
 }
 
@@ -229,6 +230,8 @@ __global__ void __launch_bounds__(kCubeThreads)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const Bits *data = static_cast<const Bits *>(a.data);
     Bits *out_cubes = static_cast<Bits *>(a.out_cubes);
+    // offset of this launch's first cube: 0, or the running total left by the previous chained launch
+    const uint32_t launch_base = a.base_words ? *a.base_words : 0u;
 
     // Work is handed out by a free-running ticket counter: ticket order == cube order, which is what
     // makes spinning on predecessors in the look-back deadlock-free (a predecessor's ticket was drawn
@@ -317,10 +320,10 @@ __global__ void __launch_bounds__(kCubeThreads)
             //      prefetch the next cube (thread 32). All are L2 round trips hidden behind phase 2.
             if (warp == 0) {
                 if (lane == 0) {
-                    ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, t == 0 ? kStatusPrefix : kStatusAggregate, cube_words));
+                    ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, kStatusAggregate, cube_words));
                 }
                 if (prev_t != kNone && prev_t != 0) {
-                    sample = look_back_load(a.desc, static_cast<int64_t>(prev_t) - 1, a.epoch, lane);
+                    sample = look_back_load(a.desc, static_cast<int64_t>(prev_t) - 1, a.epoch, lane, launch_base);
                     sampled = true;
                 }
             }
@@ -347,11 +350,13 @@ __global__ void __launch_bounds__(kCubeThreads)
 
         // ---- the previous cube: look back (it has had a whole iteration to become cheap) -------------
         if (prev_t != kNone && warp == 0) {
-            if (!sampled && prev_t != 0) sample = look_back_load(a.desc, static_cast<int64_t>(prev_t) - 1, a.epoch, lane);
-            const uint32_t exclusive = prev_t == 0 ? 0u : look_back(a.desc, prev_t, a.epoch, lane, sample);
+            if (!sampled && prev_t != 0) sample = look_back_load(a.desc, static_cast<int64_t>(prev_t) - 1, a.epoch, lane, launch_base);
+            // cube 0 starts at the launch's base offset (0, or the running total of a chained launch); its
+            // descriptor was published as an aggregate and is upgraded to a prefix here like any other
+            const uint32_t exclusive = prev_t == 0 ? launch_base : look_back(a.desc, prev_t, a.epoch, lane, sample, launch_base);
             if (lane == 0) {
                 const uint32_t after = exclusive + prev_words;
-                if (prev_t != 0) ptx::st_relaxed_gpu(a.desc + prev_t, pack_desc(a.epoch, kStatusPrefix, after));
+                ptx::st_relaxed_gpu(a.desc + prev_t, pack_desc(a.epoch, kStatusPrefix, after));
                 aux.prefix[iter & 1] = exclusive;
                 a.out_offsets[prev_t] = after;  // "offset_after", reference src/ndzip/common.hh:342-347
                 if (prev_t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452

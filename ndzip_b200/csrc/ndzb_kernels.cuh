@@ -22,7 +22,8 @@ struct compress_launch {
     void *out_cubes;           // bits_type*: where the range's first compressed cube goes
     uint32_t *out_offsets;     // inclusive word offsets, entry i belongs to cube hc_begin + i
     uint32_t *pad_word;        // nullable: header padding word to be zeroed (f64, odd H)
-    uint32_t *total_words;     // device scalar: compressed words of the whole range
+    const uint32_t *base_words; // nullable: device scalar added to every offset of this launch (chained launches)
+    uint32_t *total_words;     // device scalar: base + compressed words of the whole range
     uint32_t *length_out;      // nullable: receives length_add + total
     uint32_t length_add;
     uint64_t *desc;            // decoupled look-back descriptors, >= count entries

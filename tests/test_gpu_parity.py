@@ -216,6 +216,43 @@ def test_offloader_host_api(nz, oracle, dtype, dims):
     assert back.tobytes() == data.tobytes()
 
 
+@pytest.mark.parametrize("dtype,shape", [("float32", (96, 64, 80)), ("float64", (5 * 4096,)), ("float32", (320, 192)),
+                                         ("float64", (64, 48, 32))])
+def test_pipelined_offloader_path(nz, oracle, dtype, shape, monkeypatch):
+    # border-free extents take the chunked three-stream path; force small chunks so
+    # that several chained launches (running base offset across launches) are exercised
+    import torch
+    monkeypatch.setenv("NDZB_PIPELINE_MIN_BYTES", "1")
+    side = {1: 4096, 2: 64, 3: 16}[len(shape)]
+    row_bytes = side * int(np.prod(shape[1:])) * np.dtype(dtype).itemsize if len(shape) > 1 else side * np.dtype(dtype).itemsize
+    monkeypatch.setenv("NDZB_CHUNK_BYTES", str(2 * row_bytes))
+    data = synth.smooth(shape, dtype, seed=21)
+    expect = oracle.compress(data)
+    bits = np.uint32 if dtype == "float32" else np.uint64
+    off = nz.make_cuda_offloader(dtype, len(shape))
+    for pinned in (False, True):
+        if pinned:
+            h_in = torch.from_numpy(data.copy()).pin_memory()
+            h_stream = torch.zeros(nz.compressed_length_bound(dtype, shape), dtype=torch.int32 if dtype == "float32" else torch.int64).pin_memory()
+            h_back = torch.zeros(shape, dtype=h_in.dtype).pin_memory()
+            n = off.compress(h_in, shape, h_stream)
+            got = h_stream.numpy().view(bits)[:n]
+        else:
+            stream = np.zeros(nz.compressed_length_bound(dtype, shape), dtype=bits)
+            n = off.compress(data, shape, stream)
+            got = stream[:n]
+        assert off.last_launch_count >= 2, "expected the chunked path"
+        assert n == expect.size and np.array_equal(got, expect)
+        if pinned:
+            consumed = off.decompress(h_stream, n, h_back, shape)
+            back = h_back.numpy()
+        else:
+            back = np.zeros(shape, dtype=dtype)
+            consumed = off.decompress(stream, n, back, shape)
+        assert consumed == n and back.tobytes() == data.tobytes()
+        assert off.kernel_duration_ns > 0
+
+
 def test_sharded_cube_ranges_stitch_to_the_full_stream(nz, oracle):
     # single-GPU check of the multi-GPU building blocks
     import torch
