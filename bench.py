@@ -213,8 +213,7 @@ def cpu_sample(dtype, shape, host_full=None):
         data = np.ascontiguousarray(host_full[:rows])
     else:
         # numpy generator over the full extent's coordinates restricted to the leading rows
-        full = synth.smooth(sample_shape, dtype, seed=SEED)
-        data = full
+        data = synth.smooth(sample_shape, dtype, seed=SEED, coord_shape=shape)
     return sample_shape, data
 
 

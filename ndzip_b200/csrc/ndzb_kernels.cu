@@ -39,6 +39,7 @@ struct compress_aux {
 
 template<typename Bits>
 struct decompress_aux {
+    quad segment_total[4][32];  // 2D: running sums of the four 16-row segments, per 16-byte column strip
     uint32_t warp_total[kWarps];
     Bits warp_sum[kWarps];
 };
@@ -388,23 +389,52 @@ __global__ void __launch_bounds__(kCubeThreads)
 // decompress
 // =====================================================================================================
 
-// inclusive prefix sum along one column of the tile: elements first + k*stride, k < N
-template<typename Bits, int N>
-__device__ __forceinline__ void column_prefix(uint32_t *tile, int first, int stride) {
-    constexpr int kBatch = 16;
-    Bits acc = 0;
-#pragma unroll 1
-    for (int k0 = 0; k0 < N; k0 += kBatch) {
-        Bits v[kBatch];
-#pragma unroll
-        for (int k = 0; k < kBatch; ++k) v[k] = tile_load<Bits>(tile, first + (k0 + k) * stride);
-#pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
-            acc += v[k];
-            tile_store<Bits>(tile, first + (k0 + k) * stride, acc);
+// ---- 16-byte "unit strips": UE = 4 floats / 2 doubles that are adjacent in x --------------------------
+template<typename Bits>
+struct unit_ops {
+    static constexpr int UE = 16 / sizeof(Bits);
+    // acc += q (element-wise); returns the new running sum packed like q
+    static __device__ __forceinline__ quad accumulate(Bits (&acc)[UE], quad q) {
+        if constexpr (sizeof(Bits) == 4) {
+            acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+            return quad{acc[0], acc[1], acc[2], acc[3]};
+        } else {
+            acc[0] += (static_cast<uint64_t>(q.y) << 32) | q.x;
+            acc[1] += (static_cast<uint64_t>(q.w) << 32) | q.z;
+            return quad{static_cast<uint32_t>(acc[0]), static_cast<uint32_t>(acc[0] >> 32), static_cast<uint32_t>(acc[1]),
+                    static_cast<uint32_t>(acc[1] >> 32)};
         }
     }
-}
+    static __device__ __forceinline__ quad add(quad a, quad b) {
+        if constexpr (sizeof(Bits) == 4) {
+            return quad{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+        } else {
+            const uint64_t s0 = ((static_cast<uint64_t>(a.y) << 32) | a.x) + ((static_cast<uint64_t>(b.y) << 32) | b.x);
+            const uint64_t s1 = ((static_cast<uint64_t>(a.w) << 32) | a.z) + ((static_cast<uint64_t>(b.w) << 32) | b.z);
+            return quad{static_cast<uint32_t>(s0), static_cast<uint32_t>(s0 >> 32), static_cast<uint32_t>(s1), static_cast<uint32_t>(s1 >> 32)};
+        }
+    }
+    // undo the sign rotation (reference src/ndzip/common.hh:441-444) on a unit
+    static __device__ __forceinline__ quad rotate_back(quad v) {
+        if constexpr (sizeof(Bits) == 4) {
+            return quad{rotr1(v.x), rotr1(v.y), rotr1(v.z), rotr1(v.w)};
+        } else {
+            return quad{__funnelshift_r(v.x, v.y, 1), __funnelshift_r(v.y, v.x, 1), __funnelshift_r(v.z, v.w, 1), __funnelshift_r(v.w, v.z, 1)};
+        }
+    }
+    // store a unit of final values at element pointer p
+    template<bool Vec16>
+    static __device__ __forceinline__ void store(Bits *p, quad v) {
+        if constexpr (Vec16) {
+            ptx::stg_stream_v4(p, uint4{v.x, v.y, v.z, v.w});
+        } else if constexpr (sizeof(Bits) == 4) {
+            p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+        } else {
+            p[0] = (static_cast<uint64_t>(v.y) << 32) | v.x;
+            p[1] = (static_cast<uint64_t>(v.w) << 32) | v.z;
+        }
+    }
+};
 
 // Streams the compressed cube [begin, end) (stream words) into `buf` with cp.async so that image
 // word w lands at buf[shift + w], shift = the cube's misalignment to 16 bytes: the body moves in
@@ -534,47 +564,81 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 5 : 3) decom
         }
         // the value tile aliases the compressed image: everyone must have read before anyone writes
         __syncthreads();
-        store_run(tile, tid, r);
-        __syncthreads();
-
-        // ---- remaining axes: column prefix sums in shared memory -------------------------------------
-        if constexpr (Dims == 2) {
-            if (tid < 64) column_prefix<Bits, 64>(tile, tid, 64);
-            __syncthreads();
-        } else if constexpr (Dims == 3) {
-#pragma unroll
-            for (int q = tid; q < 256; q += kCubeThreads) column_prefix<Bits, 16>(tile, (q >> 4) * 256 + (q & 15), 16);
-            __syncthreads();
-#pragma unroll
-            for (int q = tid; q < 256; q += kCubeThreads) column_prefix<Bits, 16>(tile, q, 256);
-            __syncthreads();
-        }
-
-        // ---- rotate back and store (reference cuda_codec.inl:58-65) ----------------------------------
         const uint64_t origin = cube_origin<Dims>(a.geom, hc);
-        if constexpr (Vec16) {
-            constexpr int elems_per_unit = 16 / sizeof(Bits);
-            constexpr int units = kCubeElems / elems_per_unit;
+        using U = unit_ops<Bits>;
+        constexpr int UE = U::UE;
+
+        if constexpr (Dims == 1) {
+            // ---- rotate back and store, coalesced through the tile (reference cuda_codec.inl:58-65) ----
+            store_run(tile, tid, r);
+            __syncthreads();
+            constexpr int units = kCubeElems / UE;
 #pragma unroll 8
             for (int q = tid; q < units; q += kCubeThreads) {
-                const int e = q * elems_per_unit;
-                uint4 v = *reinterpret_cast<const uint4 *>(tile + tile_elem<Bits>(e));
-                if constexpr (sizeof(Bits) == 4) {
-                    v.x = rotr1(v.x); v.y = rotr1(v.y); v.z = rotr1(v.z); v.w = rotr1(v.w);
-                } else {
-                    const uint32_t x = v.x, z = v.z;
-                    v.x = __funnelshift_r(v.x, v.y, 1); v.y = __funnelshift_r(v.y, x, 1);
-                    v.z = __funnelshift_r(v.z, v.w, 1); v.w = __funnelshift_r(v.w, z, 1);
+                const int e = q * UE;
+                U::template store<Vec16>(data + origin + e, U::rotate_back(ld_quad(tile + tile_elem<Bits>(e))));
+            }
+        } else if constexpr (Dims == 2) {
+            // ---- y direction: 16-byte column strips x four 16-row segments, scanned in registers; the
+            //      final values go straight to global memory (no tile write-back, no separate store pass)
+            store_run(tile, tid, r);
+            __syncthreads();
+            constexpr int strips = 64 / UE;  // 16 (float) or 32 (double) strips per row
+            const int xq = tid % strips, seg = tid / strips;
+            const bool active = tid < 4 * strips;
+            quad q[16];
+            if (active) {
+                Bits acc[UE] = {};
+#pragma unroll
+                for (int k = 0; k < 16; ++k) q[k] = ld_quad(tile + tile_elem<Bits>((seg * 16 + k) * 64 + xq * UE));
+#pragma unroll
+                for (int k = 0; k < 16; ++k) q[k] = U::accumulate(acc, q[k]);
+                aux.segment_total[seg][xq] = q[15];
+            }
+            __syncthreads();
+            if (active) {
+                quad carry{0, 0, 0, 0};
+                for (int sg = 0; sg < seg; ++sg) carry = U::add(carry, aux.segment_total[sg][xq]);
+                Bits *dst = data + origin + static_cast<uint64_t>(seg * 16) * a.geom.n[2] + xq * UE;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    U::template store<Vec16>(dst, U::rotate_back(U::add(q[k], carry)));
+                    dst += a.geom.n[2];
                 }
-                ptx::stg_stream_v4(data + origin + cube_local_offset<Dims>(a.geom, e), v);
             }
         } else {
-#pragma unroll 8
-            for (int e = tid; e < kCubeElems; e += kCubeThreads) {
-                data[origin + cube_local_offset<Dims>(a.geom, e)] = rotr1(tile_load<Bits>(tile, e));
+            // ---- y direction in the tile, z direction fused with rotate + store -------------------------
+            store_run(tile, tid, r);
+            __syncthreads();
+            constexpr int xqs = 16 / UE;          // strips per 16-element row: 4 (float) or 8 (double)
+            constexpr int strips = 16 * xqs;      // 64 or 128 strips per pass
+            const int xq = tid % xqs, o = tid / xqs;  // o = z in the y pass, y in the z pass
+            if (tid < strips) {
+                Bits acc[UE] = {};
+                quad q[16];
+#pragma unroll
+                for (int y = 0; y < 16; ++y) q[y] = ld_quad(tile + tile_elem<Bits>(o * 256 + y * 16 + xq * UE));
+#pragma unroll
+                for (int y = 0; y < 16; ++y) q[y] = U::accumulate(acc, q[y]);
+#pragma unroll
+                for (int y = 1; y < 16; ++y) st_quad(tile + tile_elem<Bits>(o * 256 + y * 16 + xq * UE), q[y]);
+            }
+            __syncthreads();
+            if (tid < strips) {
+                Bits acc[UE] = {};
+                quad q[16];
+#pragma unroll
+                for (int z = 0; z < 16; ++z) q[z] = ld_quad(tile + tile_elem<Bits>(z * 256 + o * 16 + xq * UE));
+                const uint64_t plane = static_cast<uint64_t>(a.geom.n[1]) * a.geom.n[2];
+                Bits *dst = data + origin + static_cast<uint64_t>(o) * a.geom.n[2] + xq * UE;
+#pragma unroll
+                for (int z = 0; z < 16; ++z) {
+                    U::template store<Vec16>(dst, U::rotate_back(U::accumulate(acc, q[z])));
+                    dst += plane;
+                }
             }
         }
-        __syncthreads();  // tile is reused by the next cube
+        __syncthreads();  // tile is reused by the cube after next; segment totals by the next cube
     }
 }
 

@@ -93,11 +93,14 @@ def smooth_constants(seed: int, dims: int, modes: int = 6):
     return out
 
 
-def smooth(shape, dtype, seed: int = 0x5EED0002, noise: float = 1e-4) -> np.ndarray:
+def smooth(shape, dtype, seed: int = 0x5EED0002, noise: float = 1e-4, coord_shape=None) -> np.ndarray:
     """Turbulence-like field: six sine modes with a k^(-5/3) amplitude
     spectrum, hashed integer wave vectors |m_d| <= k and phases, plus `noise` * u(index), u in [-1,1).
-    Evaluated in float64, rounded to ``dtype``. Mid-range ratios (~0.6 for 3D float32)."""
+    Evaluated in float64, rounded to ``dtype``. Mid-range ratios (~0.6 for 3D float32).
+    ``coord_shape`` (default: ``shape``) is the extent the coordinates are normalised by, so that the
+    leading rows of a larger grid can be generated on their own."""
     dims = len(shape)
+    coord_shape = tuple(coord_shape) if coord_shape is not None else tuple(shape)
     n = _count(shape)
     if n == 0:
         return np.zeros(shape, dtype=dtype)
@@ -112,7 +115,7 @@ def smooth(shape, dtype, seed: int = 0x5EED0002, noise: float = 1e-4) -> np.ndar
         coords = []
         rem = idx
         for d in range(dims):
-            coords.append((rem // np.uint64(strides[d])).astype(np.float64) / float(shape[d]))
+            coords.append((rem // np.uint64(strides[d])).astype(np.float64) / float(coord_shape[d]))
             rem = rem % np.uint64(strides[d])
         acc = np.zeros(idx.size, dtype=np.float64)
         for amp, wave, phase in modes:
