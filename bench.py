@@ -401,6 +401,29 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     tc_avg, td_avg = sum(tc) / len(tc), sum(td) / len(td)
 
+    # ---- the reference's own CUDA kernels (recompiled for sm_100a) on the same buffers, rank 0 only
+    ref_cuda = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            from oracle import ReferenceCuda
+            if ReferenceCuda.available():
+                rc = ReferenceCuda(dtype, shape)
+                r_stream = torch.empty(bound, dtype=tbits, device=dev)
+                r_len = torch.zeros(1, dtype=torch.int32, device=dev)
+                r_back = torch.empty_like(d_in)
+                rtc = time_call(lambda: rc.compress(d_in.data_ptr(), r_stream.data_ptr(), r_len.data_ptr()), 5)
+                rtd = time_call(lambda: rc.decompress(r_stream.data_ptr(), r_back.data_ptr()), 5)
+                n_ref = int(r_len.cpu().numpy().view(np.uint32)[0])
+                identical = bool(n_ref == n_words and torch.equal(r_stream[:n_ref], d_stream[:n_words])
+                                 and torch.equal(r_back.view(tbits), d_in.view(tbits)))
+                ref_cuda = {"what": "reference cuda_compressor/cuda_decompressor (src/ndzip/cuda_codec.inl) recompiled for sm_100a, same buffers",
+                            "compress_ms": min(rtc), "decompress_ms": min(rtd),
+                            "compress_gbs": nbytes_rank / (min(rtc) * 1e-3) / 1e9, "decompress_gbs": nbytes_rank / (min(rtd) * 1e-3) / 1e9,
+                            "stream_identical_to_ours": identical}
+                del rc, r_stream, r_back
+        except Exception as exc:  # the baseline is optional; never fail the bench because of it
+            ref_cuda = {"error": repr(exc)[:200]}
+
     # ---- optional: final stream gather to rank 0
     gather_info = None
     if world > 1 and args.gather:
@@ -489,6 +512,8 @@ def main():
         line["e2e"] = e2e
     if gather_info:
         line["stream_gather"] = gather_info
+    if ref_cuda:
+        line["reference_cuda"] = ref_cuda
     if not args.no_cpu_baseline:
         host = d_in.cpu().numpy()
         sample_shape, data = cpu_sample(dtype, shape, host_full=host)

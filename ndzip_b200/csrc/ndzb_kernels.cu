@@ -33,8 +33,9 @@ template<typename Bits>
 struct compress_aux {
     uint64_t mbar[kSlots];
     uint32_t ticket[kSlots];
-    uint32_t warp_total[kWarps];
-    uint32_t prefix[2];
+    uint32_t warp_total[2][kWarps];  // double-buffered by iteration parity (one CTA-wide barrier per cube)
+    uint32_t prefix[2];              // stream offset of the cube being copied out ...
+    uint32_t prefix_seq[2];          // ... valid once this equals iteration + 1 (warp 0 -> everyone hand-off)
 };
 
 template<typename Bits>
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(kCubeThreads)
         }
         const uint32_t t = atomicAdd(a.ticket, 1u) - a.ticket_base;
         aux.ticket[0] = t;
+        aux.prefix_seq[0] = aux.prefix_seq[1] = 0;
         if constexpr (Path == load_path::tma) {
             if (t < a.count) issue_tma_load<Bits, Dims>(slots, &aux.mbar[0], &tmap, a.geom, a.hc_begin + t);
         }
@@ -301,15 +303,16 @@ __global__ void __launch_bounds__(kCubeThreads)
                 count = (tid & 1) == 0 ? popc_bits(head) : 0u;
             }
             const uint32_t inclusive = warp_inclusive_sum(count, lane);
-            if (lane == 31) aux.warp_total[warp] = inclusive;
+            if (lane == 31) aux.warp_total[iter & 1][warp] = inclusive;
             if (tid == kTicketThread) aux.ticket[(iter + 1) % kSlots] = next_ticket;
-            __syncthreads();  // B1: reads of the input tile done; warp totals and the next ticket visible
+            __syncthreads();  // the one CTA-wide barrier per cube: input tile reads done; warp totals,
+                              // next ticket and the previous cube's image visible
 
             uint32_t before = 0;
             cube_words = tr::chunks;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) {
-                const uint32_t wt = aux.warp_total[w];
+                const uint32_t wt = aux.warp_total[iter & 1][w];
                 cube_words += wt;
                 if (w < warp) before += wt;
             }
@@ -349,31 +352,40 @@ __global__ void __launch_bounds__(kCubeThreads)
             }
         }
 
-        // ---- the previous cube: look back (it has had a whole iteration to become cheap) -------------
-        if (prev_t != kNone && warp == 0) {
-            if (!sampled && prev_t != 0) sample = look_back_load(a.desc, static_cast<int64_t>(prev_t) - 1, a.epoch, lane, launch_base);
-            // cube 0 starts at the launch's base offset (0, or the running total of a chained launch); its
-            // descriptor was published as an aggregate and is upgraded to a prefix here like any other
-            const uint32_t exclusive = prev_t == 0 ? launch_base : look_back(a.desc, prev_t, a.epoch, lane, sample, launch_base);
-            if (lane == 0) {
-                const uint32_t after = exclusive + prev_words;
-                ptx::st_relaxed_gpu(a.desc + prev_t, pack_desc(a.epoch, kStatusPrefix, after));
-                aux.prefix[iter & 1] = exclusive;
-                a.out_offsets[prev_t] = after;  // "offset_after", reference src/ndzip/common.hh:342-347
-                if (prev_t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452
-                if (prev_t == a.count - 1) {
-                    *a.total_words = after;
-                    if (a.length_out) *a.length_out = a.length_add + after;  // cuda_codec.inl:507-511
-                }
-            }
+        else {
+            __syncthreads();  // drain iteration: separates the last cube's phase 2 from its copy-out
         }
-        __syncthreads();  // B2: this iteration's cube image and the previous cube's stream offset are visible
 
-        // ---- coalesced copy of the previous cube's image to its final stream position ---------------
+        // ---- the previous cube: look back (it has had a whole iteration to become cheap) -------------
+        // Warp 0 resolves it and hands the offset to the other warps through shared memory with a
+        // sequence number instead of a second CTA-wide barrier: nobody waits for anybody but warp 0.
         if (prev_t != kNone) {
+            uint32_t exclusive;
+            if (warp == 0) {
+                if (!sampled && prev_t != 0) sample = look_back_load(a.desc, static_cast<int64_t>(prev_t) - 1, a.epoch, lane, launch_base);
+                exclusive = prev_t == 0 ? launch_base : look_back(a.desc, prev_t, a.epoch, lane, sample, launch_base);
+                if (lane == 0) {
+                    const uint32_t after = exclusive + prev_words;
+                    ptx::st_relaxed_gpu(a.desc + prev_t, pack_desc(a.epoch, kStatusPrefix, after));
+                    *const_cast<volatile uint32_t *>(&aux.prefix[iter & 1]) = exclusive;
+                    __threadfence_block();
+                    *const_cast<volatile uint32_t *>(&aux.prefix_seq[iter & 1]) = iter + 1;
+                    a.out_offsets[prev_t] = after;  // "offset_after", reference src/ndzip/common.hh:342-347
+                    if (prev_t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452
+                    if (prev_t == a.count - 1) {
+                        *a.total_words = after;
+                        if (a.length_out) *a.length_out = a.length_add + after;  // cuda_codec.inl:507-511
+                    }
+                }
+            } else {
+                while (*const_cast<volatile uint32_t *>(&aux.prefix_seq[iter & 1]) != iter + 1) {}
+                __threadfence_block();
+                exclusive = *const_cast<volatile uint32_t *>(&aux.prefix[iter & 1]);
+            }
+            // ---- coalesced copy of the previous cube's image to its final stream position -----------
             constexpr int w32 = sizeof(Bits) / 4;
             const uint32_t *src = slots + prev_slot * slot_words;
-            uint32_t *dst = reinterpret_cast<uint32_t *>(out_cubes + aux.prefix[iter & 1]);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(out_cubes + exclusive);
             const int n = static_cast<int>(prev_words) * w32;
 #pragma unroll 4
             for (int w = tid; w < n; w += kCubeThreads) dst[w] = src[w];
@@ -472,18 +484,24 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 5 : 3) decom
 
     // Cubes are independent: static round-robin over the grid. The stream offsets of a cube are read
     // two iterations ahead and its compressed words are streamed in one iteration ahead.
-    auto offsets_of = [&](uint32_t t, uint32_t &begin, uint32_t &end) {
-        begin = end = 0;
+    // Even lanes hold `begin`, odd lanes `end`: a lane-dependent address keeps the value in an ordinary
+    // register until it is shuffled out at its use. (With a CTA-uniform address ptxas moves the result
+    // into a uniform register right behind the load and the "prefetch" stalls for the full L2 latency:
+    // 13.5 % of all samples in profiles/r1_r1d_decompress.txt.)
+    auto offsets_of = [&](uint32_t t) -> uint32_t {
+        uint32_t v = 0;
         if (t < a.count) {
             const uint32_t hc = a.hc_begin + t;
-            begin = hc ? __ldg(a.offsets + hc - 1) : 0u;  // reference src/ndzip/common.hh:350-358
-            end = __ldg(a.offsets + hc);
+            const uint32_t odd = lane & 1;
+            if (odd || hc) v = __ldg(a.offsets + hc - 1 + odd);  // reference src/ndzip/common.hh:350-358
         }
+        return v;
     };
-    uint32_t cur_begin, cur_end, next_begin, next_end;
-    offsets_of(blockIdx.x, cur_begin, cur_end);
-    offsets_of(blockIdx.x + gridDim.x, next_begin, next_end);
-    if (blockIdx.x < a.count) stream_in_cube<Bits>(bufs, stream_cubes, cur_begin, cur_end, tid);
+    uint32_t cur_offsets = offsets_of(blockIdx.x);
+    uint32_t next_offsets = offsets_of(blockIdx.x + gridDim.x);
+    if (blockIdx.x < a.count) {
+        stream_in_cube<Bits>(bufs, stream_cubes, __shfl_sync(kFullMask, cur_offsets, 0), __shfl_sync(kFullMask, cur_offsets, 1), tid);
+    }
     ptx::cp_async_commit();
 
     for (uint32_t k = 0, t = blockIdx.x; t < a.count; ++k, t += gridDim.x) {
@@ -491,12 +509,14 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 5 : 3) decom
         uint32_t *tile = bufs + (k & 1) * buf_words;
         // prefetch: next cube's words into the other buffer (free since the end of the previous iteration),
         // the cube after that's offsets into registers
-        if (t + gridDim.x < a.count) stream_in_cube<Bits>(bufs + ((k + 1) & 1) * buf_words, stream_cubes, next_begin, next_end, tid);
+        if (t + gridDim.x < a.count) {
+            stream_in_cube<Bits>(bufs + ((k + 1) & 1) * buf_words, stream_cubes, __shfl_sync(kFullMask, next_offsets, 0),
+                    __shfl_sync(kFullMask, next_offsets, 1), tid);
+        }
         ptx::cp_async_commit();
-        const uint32_t begin = cur_begin;
-        cur_begin = next_begin;
-        cur_end = next_end;
-        offsets_of(t + 2 * gridDim.x, next_begin, next_end);
+        const uint32_t begin = __shfl_sync(kFullMask, cur_offsets, 0);
+        cur_offsets = next_offsets;
+        next_offsets = offsets_of(t + 2 * gridDim.x);
 
         ptx::cp_async_wait<1>();  // everything but the newest group (the prefetch) has landed
         __syncthreads();

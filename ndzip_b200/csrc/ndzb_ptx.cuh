@@ -117,6 +117,15 @@ __device__ __forceinline__ void st_relaxed_gpu(uint64_t *p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// A read-only 32-bit load the compiler cannot see through: the result stays in an ordinary register
+// until it is used. (With __ldg of a CTA-uniform address ptxas moves the value to a uniform register
+// right after the load, which turns a prefetch into a ~1 us stall: profiles/r1_r1d_decompress.txt.)
+__device__ __forceinline__ uint32_t ldg_u32_opaque(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // ---- streaming global access (data is touched exactly once) -------------------------------------
 __device__ __forceinline__ uint4 ldg_stream_v4(const void *p) {
     uint4 r;

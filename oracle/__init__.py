@@ -304,6 +304,50 @@ class Reference:
         return [(int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(n)]
 
 
+REFCUDA_SO = os.path.join(_HERE, "_ref", "libndzip_refcuda.so")
+
+
+class ReferenceCuda:
+    """The unmodified reference CUDA codec recompiled for sm_100a (oracle/_ref/libndzip_refcuda.so,
+    `make -C oracle refcuda`): device-pointer API of reference include/ndzip/cuda.hh:10-41."""
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REFCUDA_SO)
+
+    def __init__(self, dtype, shape, stream: int = 0, path: str = REFCUDA_SO):
+        L = ctypes.CDLL(path)
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        L.ndzrc_create.restype = vp
+        L.ndzrc_create.argtypes = [ci, ci, vp, vp]
+        L.ndzrc_destroy.argtypes = [vp]
+        L.ndzrc_compress.restype = ci
+        L.ndzrc_compress.argtypes = [vp, vp, vp, vp, vp]
+        L.ndzrc_decompress.restype = ci
+        L.ndzrc_decompress.argtypes = [vp, vp, vp, vp]
+        self.L = L
+        self.dims, self.size = _size3(shape)
+        self.h = L.ndzrc_create(dtype_code(dtype), self.dims, self.size, stream)
+        if not self.h:
+            raise RuntimeError("reference make_cuda_compressor failed")
+
+    def compress(self, d_in_ptr: int, d_stream_ptr: int, d_len_ptr: int) -> None:
+        if self.L.ndzrc_compress(self.h, d_in_ptr, self.size, d_stream_ptr, d_len_ptr) != 0:
+            raise RuntimeError("reference cuda compress failed")
+
+    def decompress(self, d_stream_ptr: int, d_out_ptr: int) -> None:
+        if self.L.ndzrc_decompress(self.h, d_stream_ptr, d_out_ptr, self.size) != 0:
+            raise RuntimeError("reference cuda decompress failed")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ndzrc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 _oracle: Optional[Oracle] = None
 _reference: Optional[Reference] = None
 

@@ -123,6 +123,39 @@ def test_zero_hypercube_extents(nz, oracle, dtype, dims, n):
     assert gpu_decompress(stream, dtype, shape).tobytes() == data.tobytes()
 
 
+@pytest.mark.parametrize("dtype,dims", PROFILES)
+def test_stream_equals_reference_cuda_encoder(nz, dtype, dims):
+    # second, GPU-side oracle: the reference's own CUDA encoder recompiled for sm_100a (when prebuilt)
+    import torch
+    from oracle import ReferenceCuda
+    if not ReferenceCuda.available():
+        pytest.skip("oracle/_ref/libndzip_refcuda.so not prebuilt")
+    shape = {1: (7 * 4096 + 33,), 2: (4 * 64 - 1, 3 * 64 + 5), 3: (63, 40, 50)}[dims]
+    data = synth.smooth(shape, dtype, seed=15)
+    tbits = torch.int32 if dtype == "float32" else torch.int64
+    d_in = torch.from_numpy(data).cuda()
+    bound = nz.compressed_length_bound(dtype, shape)
+    ours = torch.zeros(bound, dtype=tbits, device="cuda")
+    theirs = torch.zeros(bound, dtype=tbits, device="cuda")
+    n_ours = torch.zeros(1, dtype=torch.int32, device="cuda")
+    n_theirs = torch.zeros(1, dtype=torch.int32, device="cuda")
+    nz.make_cuda_compressor(dtype, shape).compress(d_in, shape, ours, n_ours)
+    ref = ReferenceCuda(dtype, shape)
+    ref.compress(d_in.data_ptr(), theirs.data_ptr(), n_theirs.data_ptr())
+    torch.cuda.synchronize()
+    n = int(n_ours.item())
+    assert n == int(n_theirs.item())
+    assert torch.equal(ours[:n], theirs[:n])
+    # cross pairing: their decoder on our stream, our decoder on their stream
+    back_a = torch.zeros_like(d_in)
+    back_b = torch.zeros_like(d_in)
+    ref.decompress(ours.data_ptr(), back_a.data_ptr())
+    nz.make_cuda_decompressor(dtype, dims).decompress(theirs, back_b, shape)
+    torch.cuda.synchronize()
+    assert torch.equal(back_a.view(tbits), d_in.view(tbits))
+    assert torch.equal(back_b.view(tbits), d_in.view(tbits))
+
+
 def test_header_padding_word_is_zero(nz):
     # f64 with an odd cube count: the GPU encoders write 0 to the padding word (cuda_codec.inl:446-452)
     from gpu_util import gpu_compress
