@@ -12,6 +12,7 @@ run golden_f32 -k "golden_fixture and float32"
 run golden_f64 -k "golden_fixture and float64"
 run oracle_f32 -k "stream_equals_oracle and float32"
 run oracle_f64 -k "stream_equals_oracle and float64"
-run misc -k "not golden_fixture and not stream_equals_oracle and not baseline_config"
+run misc -k "not golden_fixture and not stream_equals_oracle and not baseline_config and not large_configs"
 run baseline -k "baseline_config"
+run large -k "large_configs"
 timeout 600 python -m pytest tests/test_cpp_adapter.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_adapter.log 2>&1; echo "[adapter] rc=$? $(tail -1 gpurun_out/pytest_adapter.log)"

@@ -376,3 +376,67 @@ def test_baseline_config_roundtrip_and_reference_parity(nz, dtype, shape):
         got = d_stream[:n].cpu().numpy().view(bits)
         assert zlib.crc32(got.tobytes()) == zlib.crc32(expect[:n].tobytes())
         assert np.array_equal(got, expect[:n])
+
+
+# Configs 4 and 5 of BASELINE.json at their full single-GPU-resident sizes (8 GiB of input): too large
+# for a CPU oracle pass inside a test, so they are checked through size-independent properties —
+# exact device round trip, header monotonicity within [C, bound], stream length = header + last offset,
+# run-to-run determinism — plus stream equality against the oracle on the leading cube rows.
+LARGE_CASES = [
+    ("float64", (1024, 1024, 1024)),    # config 4: 3D fp64 1024^3 (8 GiB)
+    ("float32", (1 << 31,)),            # config 5: 1D fp32 2 Gi elements (8 GiB)
+]
+
+
+@pytest.mark.parametrize("dtype,shape", LARGE_CASES, ids=["cfg4-3d-f64-1024", "cfg5-1d-f32-2Gi"])
+def test_large_configs_properties(nz, oracle, dtype, shape):
+    import torch
+    from bench import make_device_input
+    free, _ = torch.cuda.mem_get_info()
+    itemsize = np.dtype(dtype).itemsize
+    n_bytes = int(np.prod(shape)) * itemsize
+    bound = nz.compressed_length_bound(dtype, shape)
+    need = 2 * n_bytes + 2 * bound * itemsize + (2 << 30)
+    if free < need:
+        pytest.skip(f"needs {need >> 30} GiB of device memory")
+    assert bound < 2 ** 32
+    tbits = torch.int32 if dtype == "float32" else torch.int64
+    d_in = make_device_input(dtype, shape, seed=0x5EED0004)
+    d_stream = torch.empty(bound, dtype=tbits, device="cuda")
+    d_len = torch.zeros(1, dtype=torch.int32, device="cuda")
+    comp = nz.make_cuda_compressor(dtype, shape)
+    comp.compress(d_in, shape, d_stream, d_len)
+    torch.cuda.synchronize()
+    n = int(d_len.cpu().numpy().view(np.uint32)[0])
+    H = nz.num_hypercubes(shape)
+    hdr_words = H if dtype == "float32" else (H + 1) // 2
+    header = d_stream[:hdr_words].cpu().numpy().view(np.uint32)[:H].astype(np.int64)
+    steps = np.diff(np.concatenate([[0], header]))
+    C, cube_bound = (128, 4224) if dtype == "float32" else (64, 4160)
+    assert steps.min() >= C and steps.max() <= cube_bound
+    assert n == hdr_words + int(header[-1])
+    # leading cube rows against the oracle (cube contents do not depend on the rest of the grid)
+    rows = {1: 4096 * 8, 3: 16}[len(shape)]
+    lead_shape = (rows,) + tuple(shape[1:])
+    lead = d_in[:rows].cpu().numpy()
+    expect = oracle.compress(lead)
+    H_lead = nz.num_hypercubes(lead_shape)
+    hdr_lead = H_lead if dtype == "float32" else (H_lead + 1) // 2
+    bits = np.uint32 if dtype == "float32" else np.uint64
+    assert np.array_equal(header[:H_lead].astype(np.uint32), expect[:hdr_lead].view(np.uint32)[:H_lead])
+    words_lead = int(header[H_lead - 1])
+    got = d_stream[hdr_words: hdr_words + words_lead].cpu().numpy().view(bits)
+    assert np.array_equal(got, expect[hdr_lead: hdr_lead + words_lead])
+    del lead, expect, got
+    # exact round trip on the device
+    d_back = torch.empty_like(d_in)
+    nz.make_cuda_decompressor(dtype, len(shape)).decompress(d_stream, d_back, shape)
+    torch.cuda.synchronize()
+    assert torch.equal(d_in.view(tbits), d_back.view(tbits))
+    del d_back
+    # determinism
+    d_stream2 = torch.empty(bound, dtype=tbits, device="cuda")
+    comp.compress(d_in, shape, d_stream2, d_len)
+    torch.cuda.synchronize()
+    assert int(d_len.cpu().numpy().view(np.uint32)[0]) == n
+    assert torch.equal(d_stream[:n], d_stream2[:n])
