@@ -332,17 +332,17 @@ def main():
     dec = nz.make_cuda_decompressor(dtype, len(shape))
     launches = 0
 
+    d_gathered = torch.zeros(world, dtype=torch.int32, device=dev)
+    d_overhead = torch.full((world,), hdr_words + nzd.border_in(shape), dtype=torch.int32, device=dev)
+    local_header = d_stream[:hdr_words].view(torch.int32)
+
     def exchange():
-        """cross-rank exclusive scan of compressed word counts + header fix-up (N>1 only)"""
+        """cross-rank exclusive scan of compressed word counts + header fix-up (N>1 only):
+        one NCCL all-gather of every rank's stream length, one fix-up kernel"""
         if world == 1:
             return 0
-        cube_words = (d_len.to(torch.int64) - hdr_words)
-        gathered = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gathered, cube_words)
-        base = torch.cumsum(gathered, 0)[rank] - gathered[rank]
-        d_base.copy_(base.to(torch.int32))
-        d_header_global.copy_(d_stream[:hdr_words].view(torch.int32)[:H])
-        comp.add_offset(d_header_global, H, d_base)
+        dist.all_gather_into_tensor(d_gathered, d_len)
+        comp.fixup_header(local_header, d_header_global, H, d_gathered, d_overhead, rank)
         return 1
 
     def step():

@@ -84,6 +84,11 @@ int ndzb_offload_decompress(ndzb_ctx *ctx, const void *h_stream, uint32_t length
 int ndzb_compress_cubes(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t *size, uint32_t hc_begin,
         uint32_t hc_end, void *d_cubes, uint32_t *d_offsets_after, uint32_t *d_local_words);
 int ndzb_add_offset(ndzb_ctx *ctx, uint32_t *d_offsets, uint32_t count, const uint32_t *d_base_words);
+/* The exchange step in one launch: given the all-gathered stream lengths of every rank (d_gathered_lengths,
+ * words) and every rank's non-cube words (header + border, d_overhead_words), writes this rank's global
+ * header entries: d_global_header[i] = d_local_header[i] + sum over lower ranks of their cube words. */
+int ndzb_fixup_header(ndzb_ctx *ctx, const uint32_t *d_local_header, uint32_t *d_global_header, uint32_t count,
+        const uint32_t *d_gathered_lengths, const uint32_t *d_overhead_words, uint32_t rank);
 /* Copies the border elements of `size` (raw bits, ascending linear index) to d_out; needs the whole
  * array addressable from d_data. Returns nothing on an extent without border. */
 int ndzb_pack_border(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t *size, void *d_out);

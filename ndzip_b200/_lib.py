@@ -22,6 +22,7 @@ SYMBOLS = [
     ("ndzb_offload_decompress", _i, [_vp, _vp, _u32, _vp, _i, _vp, _pu32, _pu64]),
     ("ndzb_compress_cubes", _i, [_vp, _vp, _i, _vp, _u32, _u32, _vp, _vp, _vp]),
     ("ndzb_add_offset", _i, [_vp, _vp, _u32, _vp]),
+    ("ndzb_fixup_header", _i, [_vp, _vp, _vp, _u32, _vp, _vp, _u32]),
     ("ndzb_pack_border", _i, [_vp, _vp, _i, _vp, _vp]),
     ("ndzb_decompress_cubes", _i, [_vp, _vp, _vp, _i, _vp, _u32, _u32]),
     ("ndzb_num_hypercubes", _u32, [_i, _vp]),

@@ -154,6 +154,11 @@ class cuda_compressor(_context):
     def add_offset(self, offsets, count: int, base_words) -> None:
         _lib.check(self._lib.ndzb_add_offset(self._handle, _ptr(offsets), count, _ptr(base_words)))
 
+    def fixup_header(self, local_header, global_header, count: int, gathered_lengths, overhead_words, rank: int) -> None:
+        """Multi-GPU exchange step after the all-gather of stream lengths (include/ndzip_b200.h)."""
+        _lib.check(self._lib.ndzb_fixup_header(self._handle, _ptr(local_header), _ptr(global_header), count,
+                                               _ptr(gathered_lengths), _ptr(overhead_words), rank))
+
     def pack_border(self, in_device_data, data_size, out) -> None:
         dims, sz = _lib.size3(data_size)
         _lib.check(self._lib.ndzb_pack_border(self._handle, _ptr(in_device_data), dims, sz, _ptr(out)))

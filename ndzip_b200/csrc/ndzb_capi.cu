@@ -529,6 +529,16 @@ int ndzb_add_offset(ndzb_ctx *ctx, uint32_t *d_offsets, uint32_t count, const ui
     return NDZB_OK;
 }
 
+int ndzb_fixup_header(ndzb_ctx *ctx, const uint32_t *d_local_header, uint32_t *d_global_header, uint32_t count,
+        const uint32_t *d_gathered_lengths, const uint32_t *d_overhead_words, uint32_t rank) {
+    if (!ctx || (count && (!d_local_header || !d_global_header)) || (rank && (!d_gathered_lengths || !d_overhead_words))) {
+        return NDZB_ERR_INVALID_ARGUMENT;
+    }
+    const cudaError_t e = launch_fixup_header(d_local_header, d_global_header, count, d_gathered_lengths, d_overhead_words, rank, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "fixup_header launch");
+    return NDZB_OK;
+}
+
 int ndzb_pack_border(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t *size, void *d_out) {
     if (int rc = check_call(ctx, dims, size)) return rc;
     const border_geom bg = make_border(dims, size);

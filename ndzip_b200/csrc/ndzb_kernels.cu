@@ -33,14 +33,13 @@ template<typename Bits>
 struct compress_aux {
     uint64_t mbar[kSlots];
     uint32_t ticket[kSlots];
-    uint32_t warp_total[2][kWarps];  // double-buffered by iteration parity (one CTA-wide barrier per cube)
-    uint32_t prefix[2];              // stream offset of the cube being copied out ...
-    uint32_t prefix_seq[2];          // ... valid once this equals iteration + 1 (warp 0 -> everyone hand-off)
+    uint32_t warp_total[kWarps];
+    uint32_t prefix[2];
 };
 
 template<typename Bits>
 struct decompress_aux {
-    quad segment_total[4][32];  // 2D: running sums of the four 16-row segments, per 16-byte column strip
+    Bits segment_total[4][64];  // 2D: totals of the four 16-row segments of every column
     uint32_t warp_total[kWarps];
     Bits warp_sum[kWarps];
 };
@@ -246,8 +245,13 @@ __global__ void __launch_bounds__(kCubeThreads)
     //   gets a full iteration of slack. (Waiting first made the time from drawing a ticket to publishing
     //   its length depend on other cubes' look-backs: a convoy, 57 polls per cube.)
     // * Thread 32 owns tickets and TMA: the ticket for iteration i+1 is drawn at the top of iteration i
-    //   and its TMA is issued right after barrier B1; warp 0 owns the look-back. Letting every warp
-    //   resolve the look-back itself (no second barrier) was measured and is slower (redundant polls).
+    //   and its TMA is issued right after barrier B1; warp 0 owns the look-back (sampled at B1, resolved
+    //   after phase 2) and hands the offset over at barrier B2.
+    // * Measured alternatives that were NOT better over the five BASELINE configs (profiles/README.md):
+    //   every warp resolving the look-back itself (r1f), a shared-memory hand-off instead of B2 (r1h),
+    //   a fifth "control" warp for tickets/TMA/look-back (r1i), the same with an early non-blocking
+    //   look-back attempt (r1j), a 128-wide look-back window. The other warps wait for the look-back
+    //   ~20 % of their time in all of them; what is left is L2 latency of the descriptor polls.
     constexpr int kTicketThread = 32;
     if (tid == kTicketThread) {
         if constexpr (Path == load_path::tma) {
@@ -257,7 +261,6 @@ __global__ void __launch_bounds__(kCubeThreads)
         }
         const uint32_t t = atomicAdd(a.ticket, 1u) - a.ticket_base;
         aux.ticket[0] = t;
-        aux.prefix_seq[0] = aux.prefix_seq[1] = 0;
         if constexpr (Path == load_path::tma) {
             if (t < a.count) issue_tma_load<Bits, Dims>(slots, &aux.mbar[0], &tmap, a.geom, a.hc_begin + t);
         }
@@ -303,16 +306,15 @@ __global__ void __launch_bounds__(kCubeThreads)
                 count = (tid & 1) == 0 ? popc_bits(head) : 0u;
             }
             const uint32_t inclusive = warp_inclusive_sum(count, lane);
-            if (lane == 31) aux.warp_total[iter & 1][warp] = inclusive;
+            if (lane == 31) aux.warp_total[warp] = inclusive;
             if (tid == kTicketThread) aux.ticket[(iter + 1) % kSlots] = next_ticket;
-            __syncthreads();  // the one CTA-wide barrier per cube: input tile reads done; warp totals,
-                              // next ticket and the previous cube's image visible
+            __syncthreads();  // B1: reads of the input tile done; warp totals and the next ticket visible
 
             uint32_t before = 0;
             cube_words = tr::chunks;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) {
-                const uint32_t wt = aux.warp_total[iter & 1][w];
+                const uint32_t wt = aux.warp_total[w];
                 cube_words += wt;
                 if (w < warp) before += wt;
             }
@@ -352,40 +354,31 @@ __global__ void __launch_bounds__(kCubeThreads)
             }
         }
 
-        else {
-            __syncthreads();  // drain iteration: separates the last cube's phase 2 from its copy-out
-        }
-
         // ---- the previous cube: look back (it has had a whole iteration to become cheap) -------------
-        // Warp 0 resolves it and hands the offset to the other warps through shared memory with a
-        // sequence number instead of a second CTA-wide barrier: nobody waits for anybody but warp 0.
-        if (prev_t != kNone) {
-            uint32_t exclusive;
-            if (warp == 0) {
-                if (!sampled && prev_t != 0) sample = look_back_load(a.desc, static_cast<int64_t>(prev_t) - 1, a.epoch, lane, launch_base);
-                exclusive = prev_t == 0 ? launch_base : look_back(a.desc, prev_t, a.epoch, lane, sample, launch_base);
-                if (lane == 0) {
-                    const uint32_t after = exclusive + prev_words;
-                    ptx::st_relaxed_gpu(a.desc + prev_t, pack_desc(a.epoch, kStatusPrefix, after));
-                    *const_cast<volatile uint32_t *>(&aux.prefix[iter & 1]) = exclusive;
-                    __threadfence_block();
-                    *const_cast<volatile uint32_t *>(&aux.prefix_seq[iter & 1]) = iter + 1;
-                    a.out_offsets[prev_t] = after;  // "offset_after", reference src/ndzip/common.hh:342-347
-                    if (prev_t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452
-                    if (prev_t == a.count - 1) {
-                        *a.total_words = after;
-                        if (a.length_out) *a.length_out = a.length_add + after;  // cuda_codec.inl:507-511
-                    }
+        if (prev_t != kNone && warp == 0) {
+            if (!sampled && prev_t != 0) sample = look_back_load(a.desc, static_cast<int64_t>(prev_t) - 1, a.epoch, lane, launch_base);
+            // cube 0 starts at the launch's base offset (0, or the running total of a chained launch); its
+            // descriptor was published as an aggregate and is upgraded to a prefix here like any other
+            const uint32_t exclusive = prev_t == 0 ? launch_base : look_back(a.desc, prev_t, a.epoch, lane, sample, launch_base);
+            if (lane == 0) {
+                const uint32_t after = exclusive + prev_words;
+                ptx::st_relaxed_gpu(a.desc + prev_t, pack_desc(a.epoch, kStatusPrefix, after));
+                aux.prefix[iter & 1] = exclusive;
+                a.out_offsets[prev_t] = after;  // "offset_after", reference src/ndzip/common.hh:342-347
+                if (prev_t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452
+                if (prev_t == a.count - 1) {
+                    *a.total_words = after;
+                    if (a.length_out) *a.length_out = a.length_add + after;  // cuda_codec.inl:507-511
                 }
-            } else {
-                while (*const_cast<volatile uint32_t *>(&aux.prefix_seq[iter & 1]) != iter + 1) {}
-                __threadfence_block();
-                exclusive = *const_cast<volatile uint32_t *>(&aux.prefix[iter & 1]);
             }
-            // ---- coalesced copy of the previous cube's image to its final stream position -----------
+        }
+        __syncthreads();  // B2: this iteration's cube image and the previous cube's stream offset are visible
+
+        // ---- coalesced copy of the previous cube's image to its final stream position ---------------
+        if (prev_t != kNone) {
             constexpr int w32 = sizeof(Bits) / 4;
             const uint32_t *src = slots + prev_slot * slot_words;
-            uint32_t *dst = reinterpret_cast<uint32_t *>(out_cubes + exclusive);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(out_cubes + aux.prefix[iter & 1]);
             const int n = static_cast<int>(prev_words) * w32;
 #pragma unroll 4
             for (int w = tid; w < n; w += kCubeThreads) dst[w] = src[w];
@@ -401,49 +394,46 @@ __global__ void __launch_bounds__(kCubeThreads)
 // decompress
 // =====================================================================================================
 
-// ---- 16-byte "unit strips": UE = 4 floats / 2 doubles that are adjacent in x --------------------------
+// ---- column strips: two x-adjacent elements per thread (8 bytes float, 16 bytes double), so that the
+// 4096-element cube gives all 128 threads a strip in every pass --------------------------------------
 template<typename Bits>
-struct unit_ops {
-    static constexpr int UE = 16 / sizeof(Bits);
-    // acc += q (element-wise); returns the new running sum packed like q
-    static __device__ __forceinline__ quad accumulate(Bits (&acc)[UE], quad q) {
+struct strip {
+    Bits v[2];
+
+    static __device__ __forceinline__ strip load(const uint32_t *tile, int e) {  // e even
+        strip s;
         if constexpr (sizeof(Bits) == 4) {
-            acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
-            return quad{acc[0], acc[1], acc[2], acc[3]};
+            const uint2 q = *reinterpret_cast<const uint2 *>(tile + tile_elem<Bits>(e));
+            s.v[0] = q.x;
+            s.v[1] = q.y;
         } else {
-            acc[0] += (static_cast<uint64_t>(q.y) << 32) | q.x;
-            acc[1] += (static_cast<uint64_t>(q.w) << 32) | q.z;
-            return quad{static_cast<uint32_t>(acc[0]), static_cast<uint32_t>(acc[0] >> 32), static_cast<uint32_t>(acc[1]),
-                    static_cast<uint32_t>(acc[1] >> 32)};
+            const quad q = ld_quad(tile + tile_elem<Bits>(e));
+            s.v[0] = (static_cast<uint64_t>(q.y) << 32) | q.x;
+            s.v[1] = (static_cast<uint64_t>(q.w) << 32) | q.z;
+        }
+        return s;
+    }
+    __device__ __forceinline__ void store(uint32_t *tile, int e) const {
+        if constexpr (sizeof(Bits) == 4) {
+            *reinterpret_cast<uint2 *>(tile + tile_elem<Bits>(e)) = uint2{v[0], v[1]};
+        } else {
+            st_quad(tile + tile_elem<Bits>(e), quad{static_cast<uint32_t>(v[0]), static_cast<uint32_t>(v[0] >> 32),
+                                                     static_cast<uint32_t>(v[1]), static_cast<uint32_t>(v[1] >> 32)});
         }
     }
-    static __device__ __forceinline__ quad add(quad a, quad b) {
-        if constexpr (sizeof(Bits) == 4) {
-            return quad{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
-        } else {
-            const uint64_t s0 = ((static_cast<uint64_t>(a.y) << 32) | a.x) + ((static_cast<uint64_t>(b.y) << 32) | b.x);
-            const uint64_t s1 = ((static_cast<uint64_t>(a.w) << 32) | a.z) + ((static_cast<uint64_t>(b.w) << 32) | b.z);
-            return quad{static_cast<uint32_t>(s0), static_cast<uint32_t>(s0 >> 32), static_cast<uint32_t>(s1), static_cast<uint32_t>(s1 >> 32)};
-        }
-    }
-    // undo the sign rotation (reference src/ndzip/common.hh:441-444) on a unit
-    static __device__ __forceinline__ quad rotate_back(quad v) {
-        if constexpr (sizeof(Bits) == 4) {
-            return quad{rotr1(v.x), rotr1(v.y), rotr1(v.z), rotr1(v.w)};
-        } else {
-            return quad{__funnelshift_r(v.x, v.y, 1), __funnelshift_r(v.y, v.x, 1), __funnelshift_r(v.z, v.w, 1), __funnelshift_r(v.w, v.z, 1)};
-        }
-    }
-    // store a unit of final values at element pointer p
-    template<bool Vec16>
-    static __device__ __forceinline__ void store(Bits *p, quad v) {
-        if constexpr (Vec16) {
-            ptx::stg_stream_v4(p, uint4{v.x, v.y, v.z, v.w});
+    __device__ __forceinline__ strip operator+(const strip &o) const { return strip{{v[0] + o.v[0], v[1] + o.v[1]}}; }
+    // undo the sign rotation (reference src/ndzip/common.hh:441-444) and write the final values at p
+    template<bool Vec>
+    __device__ __forceinline__ void emit(Bits *p) const {
+        const Bits a = rotr1(v[0]), b = rotr1(v[1]);
+        if constexpr (!Vec) {
+            p[0] = a;
+            p[1] = b;
         } else if constexpr (sizeof(Bits) == 4) {
-            p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+            asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
         } else {
-            p[0] = (static_cast<uint64_t>(v.y) << 32) | v.x;
-            p[1] = (static_cast<uint64_t>(v.w) << 32) | v.z;
+            ptx::stg_stream_v4(p, uint4{static_cast<uint32_t>(a), static_cast<uint32_t>(a >> 32), static_cast<uint32_t>(b),
+                                        static_cast<uint32_t>(b >> 32)});
         }
     }
 };
@@ -585,76 +575,78 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 5 : 3) decom
         // the value tile aliases the compressed image: everyone must have read before anyone writes
         __syncthreads();
         const uint64_t origin = cube_origin<Dims>(a.geom, hc);
-        using U = unit_ops<Bits>;
-        constexpr int UE = U::UE;
+        using S = strip<Bits>;
 
         if constexpr (Dims == 1) {
             // ---- rotate back and store, coalesced through the tile (reference cuda_codec.inl:58-65) ----
             store_run(tile, tid, r);
             __syncthreads();
+            constexpr int UE = 16 / sizeof(Bits);
             constexpr int units = kCubeElems / UE;
 #pragma unroll 8
             for (int q = tid; q < units; q += kCubeThreads) {
                 const int e = q * UE;
-                U::template store<Vec16>(data + origin + e, U::rotate_back(ld_quad(tile + tile_elem<Bits>(e))));
-            }
-        } else if constexpr (Dims == 2) {
-            // ---- y direction: 16-byte column strips x four 16-row segments, scanned in registers; the
-            //      final values go straight to global memory (no tile write-back, no separate store pass)
-            store_run(tile, tid, r);
-            __syncthreads();
-            constexpr int strips = 64 / UE;  // 16 (float) or 32 (double) strips per row
-            const int xq = tid % strips, seg = tid / strips;
-            const bool active = tid < 4 * strips;
-            quad q[16];
-            if (active) {
-                Bits acc[UE] = {};
-#pragma unroll
-                for (int k = 0; k < 16; ++k) q[k] = ld_quad(tile + tile_elem<Bits>((seg * 16 + k) * 64 + xq * UE));
-#pragma unroll
-                for (int k = 0; k < 16; ++k) q[k] = U::accumulate(acc, q[k]);
-                aux.segment_total[seg][xq] = q[15];
-            }
-            __syncthreads();
-            if (active) {
-                quad carry{0, 0, 0, 0};
-                for (int sg = 0; sg < seg; ++sg) carry = U::add(carry, aux.segment_total[sg][xq]);
-                Bits *dst = data + origin + static_cast<uint64_t>(seg * 16) * a.geom.n[2] + xq * UE;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    U::template store<Vec16>(dst, U::rotate_back(U::add(q[k], carry)));
-                    dst += a.geom.n[2];
+                const quad v = ld_quad(tile + tile_elem<Bits>(e));
+                if constexpr (sizeof(Bits) == 4) {
+                    const quad o{rotr1(v.x), rotr1(v.y), rotr1(v.z), rotr1(v.w)};
+                    if constexpr (Vec16) ptx::stg_stream_v4(data + origin + e, uint4{o.x, o.y, o.z, o.w});
+                    else { data[origin + e] = o.x; data[origin + e + 1] = o.y; data[origin + e + 2] = o.z; data[origin + e + 3] = o.w; }
+                } else {
+                    const uint64_t a0 = rotr1((static_cast<uint64_t>(v.y) << 32) | v.x), a1 = rotr1((static_cast<uint64_t>(v.w) << 32) | v.z);
+                    if constexpr (Vec16) ptx::stg_stream_v4(data + origin + e, uint4{static_cast<uint32_t>(a0), static_cast<uint32_t>(a0 >> 32), static_cast<uint32_t>(a1), static_cast<uint32_t>(a1 >> 32)});
+                    else { data[origin + e] = a0; data[origin + e + 1] = a1; }
                 }
             }
-        } else {
-            // ---- y direction in the tile, z direction fused with rotate + store -------------------------
+        } else if constexpr (Dims == 2) {
+            // ---- y direction: 32 two-element column strips x four 16-row segments = 128 threads, scanned
+            //      in registers; final values go straight to global memory (no tile write-back)
             store_run(tile, tid, r);
             __syncthreads();
-            constexpr int xqs = 16 / UE;          // strips per 16-element row: 4 (float) or 8 (double)
-            constexpr int strips = 16 * xqs;      // 64 or 128 strips per pass
-            const int xq = tid % xqs, o = tid / xqs;  // o = z in the y pass, y in the z pass
-            if (tid < strips) {
-                Bits acc[UE] = {};
-                quad q[16];
+            const int xq = tid & 31, seg = tid >> 5;
+            S q[16];
 #pragma unroll
-                for (int y = 0; y < 16; ++y) q[y] = ld_quad(tile + tile_elem<Bits>(o * 256 + y * 16 + xq * UE));
+            for (int k = 0; k < 16; ++k) q[k] = S::load(tile, (seg * 16 + k) * 64 + xq * 2);
 #pragma unroll
-                for (int y = 0; y < 16; ++y) q[y] = U::accumulate(acc, q[y]);
+            for (int k = 1; k < 16; ++k) q[k] = q[k] + q[k - 1];
+            aux.segment_total[seg][2 * xq] = q[15].v[0];
+            aux.segment_total[seg][2 * xq + 1] = q[15].v[1];
+            __syncthreads();
+            S carry{{0, 0}};
+            for (int sg = 0; sg < seg; ++sg) carry = carry + S{{aux.segment_total[sg][2 * xq], aux.segment_total[sg][2 * xq + 1]}};
+            Bits *dst = data + origin + static_cast<uint64_t>(seg * 16) * a.geom.n[2] + xq * 2;
 #pragma unroll
-                for (int y = 1; y < 16; ++y) st_quad(tile + tile_elem<Bits>(o * 256 + y * 16 + xq * UE), q[y]);
+            for (int k = 0; k < 16; ++k) {
+                (q[k] + carry).template emit<Vec16>(dst);
+                dst += a.geom.n[2];
+            }
+        } else {
+            // ---- y direction in the tile, z direction fused with rotate + store; 16 x 8 strips per pass -
+            store_run(tile, tid, r);
+            __syncthreads();
+            const int xq = tid & 7, o = tid >> 3;  // o = z in the y pass, y in the z pass
+            {
+                S q[16];
+#pragma unroll
+                for (int y = 0; y < 16; ++y) q[y] = S::load(tile, o * 256 + y * 16 + xq * 2);
+#pragma unroll
+                for (int y = 1; y < 16; ++y) {
+                    q[y] = q[y] + q[y - 1];
+                    q[y].store(tile, o * 256 + y * 16 + xq * 2);
+                }
             }
             __syncthreads();
-            if (tid < strips) {
-                Bits acc[UE] = {};
-                quad q[16];
+            {
+                S q[16];
 #pragma unroll
-                for (int z = 0; z < 16; ++z) q[z] = ld_quad(tile + tile_elem<Bits>(z * 256 + o * 16 + xq * UE));
+                for (int z = 0; z < 16; ++z) q[z] = S::load(tile, z * 256 + o * 16 + xq * 2);
                 const uint64_t plane = static_cast<uint64_t>(a.geom.n[1]) * a.geom.n[2];
-                Bits *dst = data + origin + static_cast<uint64_t>(o) * a.geom.n[2] + xq * UE;
+                Bits *dst = data + origin + static_cast<uint64_t>(o) * a.geom.n[2] + xq * 2;
+                q[0].template emit<Vec16>(dst);
 #pragma unroll
-                for (int z = 0; z < 16; ++z) {
-                    U::template store<Vec16>(dst, U::rotate_back(U::accumulate(acc, q[z])));
+                for (int z = 1; z < 16; ++z) {
+                    q[z] = q[z] + q[z - 1];
                     dst += plane;
+                    q[z].template emit<Vec16>(dst);
                 }
             }
         }
@@ -689,6 +681,17 @@ __global__ void unpack_border_kernel(const Bits *stream_words, const uint32_t *o
 __global__ void add_offset_kernel(uint32_t *offsets, uint32_t count, const uint32_t *base) {
     const uint32_t b = *base;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) offsets[i] += b;
+}
+
+// Multi-GPU header fix-up in one launch: every rank holds the all-gathered stream lengths (words) of all
+// ranks; its cubes start after the compressed cube words of the lower ranks.
+__global__ void fixup_header_kernel(const uint32_t *local_header, uint32_t *global_header, uint32_t count,
+        const uint32_t *gathered_lengths, const uint32_t *overhead_words, uint32_t rank) {
+    uint32_t base = 0;
+    for (uint32_t r = 0; r < rank; ++r) base += gathered_lengths[r] - overhead_words[r];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        global_header[i] = local_header[i] + base;
+    }
 }
 
 __global__ void store_length_kernel(uint32_t *length_out, uint32_t value, const uint32_t *plus) {
@@ -813,6 +816,14 @@ cudaError_t launch_add_offset(uint32_t *offsets, uint32_t count, const uint32_t 
     if (count == 0) return cudaSuccess;
     const uint32_t blocks = (count + 255) / 256;
     add_offset_kernel<<<blocks < 1184u ? blocks : 1184u, 256, 0, stream>>>(offsets, count, base);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fixup_header(const uint32_t *local_header, uint32_t *global_header, uint32_t count,
+        const uint32_t *gathered_lengths, const uint32_t *overhead_words, uint32_t rank, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    const uint32_t blocks = (count + 255) / 256;
+    fixup_header_kernel<<<blocks < 592u ? blocks : 592u, 256, 0, stream>>>(local_header, global_header, count, gathered_lengths, overhead_words, rank);
     return cudaGetLastError();
 }
 

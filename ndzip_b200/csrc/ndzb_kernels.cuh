@@ -67,6 +67,9 @@ cudaError_t launch_unpack_border(int dtype, const void *stream_words, const uint
 
 // offsets[i] += *base for i < count; also used to store a constant length.
 cudaError_t launch_add_offset(uint32_t *offsets, uint32_t count, const uint32_t *base, cudaStream_t stream);
+// global_header[i] = local_header[i] + sum_{r<rank}(gathered_lengths[r] - overhead_words[r])
+cudaError_t launch_fixup_header(const uint32_t *local_header, uint32_t *global_header, uint32_t count,
+        const uint32_t *gathered_lengths, const uint32_t *overhead_words, uint32_t rank, cudaStream_t stream);
 cudaError_t launch_store_length(uint32_t *length_out, uint32_t value, const uint32_t *plus, cudaStream_t stream);
 
 // TMA tensor map for the compress input tile of (dtype, dims); returns false if the shape / pointer

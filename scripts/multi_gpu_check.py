@@ -45,10 +45,18 @@ def main():
         hdr = nzd.header_words(dtype, H)
         cube_words = d_len.to(torch.int64) - hdr - nzd.border_in(local_shape)
         layout = nzd.exchange_layout(dtype, shape, cube_words)
-        header32 = d_stream[:hdr].view(torch.int32)[:H].clone()
-        base = torch.tensor([layout.cube_word_base], dtype=torch.int32, device=dev)
+        # the exchange step as bench.py does it: all-gather the stream lengths, one fix-up kernel
+        gathered = torch.zeros(world, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(gathered, d_len)
+        spans = nzd.slab_partition(shape, world)
+        overhead = torch.tensor([nzd.header_words(dtype, nzd.cubes_in(nzd.slab_shape(shape, sp))) + nzd.border_in(nzd.slab_shape(shape, sp))
+                                 for sp in spans], dtype=torch.int32, device=dev)
+        header32 = torch.zeros(max(H, 1), dtype=torch.int32, device=dev)
         if H:
-            comp.add_offset(header32, H, base)
+            comp.fixup_header(d_stream[:hdr].view(torch.int32), header32, H, gathered, overhead, rank)
+            check = d_stream[:hdr].view(torch.int32)[:H].clone()
+            comp.add_offset(check, H, torch.tensor([layout.cube_word_base], dtype=torch.int32, device=dev))
+            assert torch.equal(check, header32[:H]), "fixup_header and add_offset disagree"
         gathered = nzd.gather_global_stream(layout, d_stream, header32, root=0)
         # local round trip
         back = torch.empty_like(slab)
