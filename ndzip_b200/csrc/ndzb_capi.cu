@@ -100,6 +100,12 @@ struct ndzb_ctx {
     uint32_t ticket_base = 0;
     uint32_t epoch = 1;
     int forced_path = -1;             // NDZB_LOAD_PATH=tma|vec16|scalar (profiling / tests)
+    uint32_t *d_watch = nullptr;      // compress_ws_kernel watchdog record (8 words)
+    bool ws_check = false;            // NDZB_WS_CHECK=1: synchronise after every launch and report a raised watchdog as an error
+    unsigned long long *d_stats = nullptr;  // NDZB_WS_STATS=1: role/wait cycle counters of the Stats kernel variants, printed per launch
+    uint32_t ws_debug = 0;            // NDZB_WS_DEBUG: profiling aids of compress_ws_kernel (produce invalid streams)
+    bool use_ws = true;               // NDZB_COMPRESS_KERNEL=v1 selects compress_kernel also for TMA-compatible inputs
+    int ws_variant = 0;               // NDZB_WS_VARIANT=n: (encoder groups, retire warps) tuning variants
     uint32_t last_launches = 0;
     // host-pointer ("offloader") staging, grown on demand and kept across calls
     void *d_in = nullptr;
@@ -158,7 +164,8 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
         const CUresult r = make_input_tensor_map(&map, ctx->dtype, ctx->dims, d_data, g);
         if (r != CUDA_SUCCESS) return driver_fail(r, "cuTensorMapEncodeTiled");
     }
-    const int per_sm = g_config.ctas_per_sm[ctx->dtype][ctx->dims - 1][static_cast<int>(path)];
+    const bool ws = path == load_path::tma && ctx->use_ws;
+    const int per_sm = ws ? 1 : g_config.ctas_per_sm[ctx->dtype][ctx->dims - 1][static_cast<int>(path)];
     const uint64_t resident = static_cast<uint64_t>(per_sm > 0 ? per_sm : 1) * g_config.num_sms;
     const uint32_t grid = static_cast<uint32_t>(count < resident ? count : resident);
 
@@ -178,10 +185,53 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
     a.ticket = ctx->d_counters;
     a.ticket_base = ctx->ticket_base;
     a.epoch = ctx->epoch;
-    const cudaError_t e = launch_compress(ctx->dtype, ctx->dims, path, a, &map, grid, ctx->stream);
-    if (e != cudaSuccess) return cuda_fail(e, "compress_kernel launch");
+    a.watch = ctx->d_watch;
+    a.debug_flags = ctx->ws_debug;
+    a.stats = ctx->d_stats;
+    if (ws) {
+        const cudaError_t e = launch_compress_ws(ctx->dtype, ctx->dims, ctx->ws_variant, a, map, grid, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "compress_ws_kernel launch");
+        ctx->ticket_base += count + compress_ws_ticket_overdraw(ctx->dtype, ctx->ws_variant, grid);  // wraps together with the device counter
+        if (ctx->d_stats) {
+            unsigned long long h[16];
+            NDZB_CUDA(cudaStreamSynchronize(ctx->stream));
+            NDZB_CUDA(cudaMemcpy(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+            NDZB_CUDA(cudaMemset(ctx->d_stats, 0, sizeof h));
+            const double enc = h[3] ? double(h[3]) : 1.0, ret = h[11] ? double(h[11]) : 1.0, g = grid;
+            fprintf(stderr, "ws stats (cycles per cube) enc: wait_tile %.0f phase1 %.0f phase2 %.0f | loader per cube: wait_slot %.0f wait_encoders %.0f total %.0f | "
+                    "retire: wait_cube %.0f look_back %.0f copy %.0f polls/cube %.2f extra_windows/cube %.2f\n",
+                    h[0] / enc, h[1] / enc, h[2] / enc, h[4] / ret, h[5] / ret, h[6] / ret, h[8] / ret, h[9] / ret, h[10] / ret, h[12] / ret, h[13] / ret);
+            (void) g;
+        }
+        if (ctx->ws_check) {
+            std::vector<uint32_t> w(kWatchdogWords, 0u);
+            NDZB_CUDA(cudaStreamSynchronize(ctx->stream));
+            NDZB_CUDA(cudaMemcpy(w.data(), ctx->d_watch, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            if (w[0] != 0) {
+                NDZB_CUDA(cudaMemcpy(w.data(), ctx->d_watch, kWatchdogWords * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+                snprintf(g_cuda_error, sizeof g_cuda_error, "compress_ws_kernel watchdog: first code 0x%x, %u look-back + %u other waits abandoned (count %u grid %u variant %d)",
+                        w[0], w[1], w[2], count, grid, ctx->ws_variant);
+                fprintf(stderr, "%s\n", g_cuda_error);
+                if (const char *path = getenv("NDZB_WS_WATCH_DUMP")) {  // all records, one per line, for offline analysis
+                    if (FILE *f = fopen(path, "w")) {
+                        for (uint32_t i = 0; i < 4000; ++i) {
+                            const uint32_t *r = w.data() + 8 + 6 * i;
+                            if (i < 8 ? i >= w[1] : i - 8 >= w[2]) continue;
+                            fprintf(f, "0x%04x %u %u %u %u %u\n", r[0], r[1], r[2], r[3], r[4], r[5]);
+                        }
+                        fclose(f);
+                    }
+                }
+                NDZB_CUDA(cudaMemset(ctx->d_watch, 0, 7 * sizeof(uint32_t)));  // keeps [7], the mode
+                return NDZB_ERR_CUDA;
+            }
+        }
+    } else {
+        const cudaError_t e = launch_compress(ctx->dtype, ctx->dims, path, a, &map, grid, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "compress_kernel launch");
+        ctx->ticket_base += count + compress_ticket_overdraw(grid);  // wraps together with the device counter
+    }
     ctx->last_launches += 1;
-    ctx->ticket_base += count + compress_ticket_overdraw(grid);  // wraps together with the device counter
     if (++ctx->epoch >= (1u << 30)) {
         NDZB_CUDA(cudaMemsetAsync(ctx->d_desc, 0, static_cast<size_t>(ctx->desc_capacity) * sizeof(uint64_t), ctx->stream));
         ctx->epoch = 1;
@@ -416,6 +466,8 @@ int ndzb_ctx_create(ndzb_ctx **out_ctx, int dtype, int dims, uint32_t max_hyperc
         else if (!strcmp(p, "vec16")) ctx->forced_path = 1;
         else if (!strcmp(p, "scalar")) ctx->forced_path = 2;
     }
+    if (const char *p = getenv("NDZB_COMPRESS_KERNEL")) ctx->use_ws = strcmp(p, "v1") != 0;
+    if (const char *p = getenv("NDZB_WS_VARIANT")) ctx->ws_variant = atoi(p);
     auto fail = [&](int rc) {
         ndzb_ctx_destroy(ctx);
         return rc;
@@ -424,6 +476,24 @@ int ndzb_ctx_create(ndzb_ctx **out_ctx, int dtype, int dims, uint32_t max_hyperc
     if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc counters"));
     e = cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint32_t), ctx->stream);
     if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMemsetAsync counters"));
+    if (const char *p = getenv("NDZB_WS_CHECK")) ctx->ws_check = atoi(p) != 0;
+    if (const char *p = getenv("NDZB_WS_DEBUG")) ctx->ws_debug = static_cast<uint32_t>(atoi(p));
+    if (const char *p = getenv("NDZB_WS_STATS")) {
+        if (atoi(p) != 0) {
+            e = cudaMalloc(&ctx->d_stats, 16 * sizeof(unsigned long long));
+            if (e == cudaSuccess) e = cudaMemset(ctx->d_stats, 0, 16 * sizeof(unsigned long long));
+            if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc stats"));
+        }
+    }
+    e = cudaMalloc(&ctx->d_watch, kWatchdogWords * sizeof(uint32_t));
+    if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc watchdog"));
+    {
+        e = cudaMemsetAsync(ctx->d_watch, 0, kWatchdogWords * sizeof(uint32_t), ctx->stream);
+        const uint32_t mode = ctx->ws_check ? 1u : 0u;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_watch + 7, &mode, sizeof mode, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // `mode` is on the stack
+        if (e != cudaSuccess) return fail(cuda_fail(e, "watchdog init"));
+    }
     if (max_hypercubes) {
         if (int rc = ensure_descriptors(ctx, max_hypercubes)) return fail(rc);
     }
@@ -438,6 +508,8 @@ void ndzb_ctx_destroy(ndzb_ctx *ctx) {
     if (!ctx) return;
     if (ctx->d_desc) cudaFree(ctx->d_desc);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_watch) cudaFree(ctx->d_watch);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_length) cudaFree(ctx->d_length);

@@ -100,35 +100,85 @@ __device__ __forceinline__ uint32_t desc_status(uint64_t d, uint32_t epoch) {
 // typically ~100 cubes back, so a 32-wide window needs several dependent round trips (measured: 2-3).
 constexpr int kLookBackDepth = 2;
 
-struct look_back_sample {
-    uint64_t d[kLookBackDepth];
+template<int Depth>
+struct look_back_window {
+    uint64_t d[Depth];
 };
+using look_back_sample = look_back_window<kLookBackDepth>;
 
 // Loads the descriptors of the window ending at predecessor `idx` (lane l: idx-l, idx-32-l, ...).
 // Positions before cube 0 read as a published prefix equal to the launch's base offset.
-__device__ __forceinline__ look_back_sample look_back_load(const uint64_t *desc, int64_t idx, uint32_t epoch, int lane, uint32_t base) {
-    look_back_sample s;
+template<int Depth = kLookBackDepth>
+__device__ __forceinline__ look_back_window<Depth> look_back_load(const uint64_t *desc, int64_t idx, uint32_t epoch, int lane, uint32_t base) {
+    look_back_window<Depth> s;
 #pragma unroll
-    for (int k = 0; k < kLookBackDepth; ++k) {
+    for (int k = 0; k < Depth; ++k) {
         const int64_t mine = idx - 32 * k - lane;
         s.d[k] = mine >= 0 ? ptx::ld_relaxed_gpu(desc + mine) : pack_desc(epoch, kStatusPrefix, base);
     }
     return s;
 }
 
+// Spin-loop watchdog of compress_ws_kernel. watch[0] != 0 means "give up": the first waiter that has been
+// stuck for kWatchdogCycles raises the flag; every spin loop polls it. Every warp that abandons a wait
+// appends a record {code, block, thread, x, y, z} at watch[8 + 6 * i] (i < kWatchRecords), so the host sees
+// the whole wait-for graph. watch[7] == 0 (production): trap right away instead.
+constexpr long long kWatchdogCycles = 4000000000ll;  // ~2 s
+constexpr uint32_t kWatchRecords = 4000;
+constexpr uint32_t kWatchWords = 8 + 6 * kWatchRecords;
+static_assert(kWatchWords <= kWatchdogWords, "watchdog buffer too small");
+struct watchdog {
+    uint32_t *watch;
+    long long start = 0;
+    uint32_t spins = 0;
+    __device__ __forceinline__ explicit watchdog(uint32_t *w) : watch(w) {}
+    // false = keep spinning, true = abandon the wait
+    __device__ __forceinline__ bool expired(uint32_t code, uint32_t x, uint32_t y, uint32_t z) {
+        if (watch == nullptr) return false;
+        if (spins++ == 0) start = clock64();
+        if ((spins & 31u) != 0) return false;
+        const bool raised = *reinterpret_cast<volatile uint32_t *>(watch) != 0;
+        if (!raised && clock64() - start < kWatchdogCycles) return false;
+        if (!raised) {
+            atomicCAS(watch, 0u, code);
+            if (watch[7] == 0u) __trap();  // production: fail loudly (sticky CUDA error) instead of hanging or returning garbage
+        }
+        if ((threadIdx.x & 31u) == 0) {
+            // look-back waits (there are hundreds, all alike) share the first 8 record slots, the rest is for the others
+            const bool lb = code == 0x10Bu;
+            const uint32_t n = atomicAdd(watch + (lb ? 1 : 2), 1u);
+            const uint32_t i = lb ? n : 8 + n;
+            if (lb ? n < 8u : i < kWatchRecords) {
+                uint32_t *r = watch + 8 + 6 * i;
+                r[0] = code;
+                r[1] = blockIdx.x;
+                r[2] = threadIdx.x;
+                r[3] = x;
+                r[4] = y;
+                r[5] = z;
+            }
+        }
+        return true;
+    }
+};
+
 // `first` is a sample of the first window taken earlier (its L2 latency hidden behind other work).
-__device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, uint32_t epoch, int lane, look_back_sample first, uint32_t base) {
+// Returns the exclusive offset; `*aborted` (optional) is set when the watchdog gave up.
+template<int Depth = kLookBackDepth>
+__device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, uint32_t epoch, int lane, look_back_window<Depth> first,
+        uint32_t base, uint32_t *watch = nullptr, bool *aborted = nullptr, uint32_t *polls = nullptr) {
     uint32_t exclusive = 0;
     int64_t idx = static_cast<int64_t>(t) - 1;
-    look_back_sample s = first;
+    look_back_window<Depth> s = first;
+    watchdog dog(watch);
     while (true) {
-        uint32_t status[kLookBackDepth];
+        uint32_t status[Depth];
         while (true) {
             // only predecessors nearer than the nearest published prefix have to be valid
             uint32_t need_wait = 0;
             bool found = false;
 #pragma unroll
-            for (int k = 0; k < kLookBackDepth; ++k) {
+            for (int k = 0; k < Depth; ++k) {
                 status[k] = desc_status(s.d[k], epoch);
                 const uint32_t invalid = __ballot_sync(kFullMask, status[k] == 0);
                 const uint32_t prefix = __ballot_sync(kFullMask, status[k] == kStatusPrefix);
@@ -139,19 +189,35 @@ __device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, 
                 }
             }
             if (need_wait == 0) break;
+            if (__any_sync(kFullMask, dog.expired(0x10Bu, t, static_cast<uint32_t>(idx), need_wait))) {
+                if (aborted) *aborted = true;
+                return 0;
+            }
             __nanosleep(20);
-            s = look_back_load(desc, idx, epoch, lane, base);
+            if (polls) *polls += 1u;
+            s = look_back_load<Depth>(desc, idx, epoch, lane, base);
         }
 #pragma unroll
-        for (int k = 0; k < kLookBackDepth; ++k) {
+        for (int k = 0; k < Depth; ++k) {
             const uint32_t prefix_lanes = __ballot_sync(kFullMask, status[k] == kStatusPrefix);
             const int nearest = prefix_lanes ? __ffs(prefix_lanes) - 1 : 32;
             exclusive += __reduce_add_sync(kFullMask, lane <= nearest ? static_cast<uint32_t>(s.d[k]) : 0u);
             if (prefix_lanes) return exclusive;
         }
-        idx -= 32 * kLookBackDepth;
-        s = look_back_load(desc, idx, epoch, lane, base);
+        idx -= 32 * Depth;
+        if (polls) *polls += 0x10000u;
+        s = look_back_load<Depth>(desc, idx, epoch, lane, base);
     }
+}
+
+// mbarrier wait with the watchdog; false = abandoned
+__device__ __forceinline__ bool mbar_wait_watched(uint64_t *bar, uint32_t parity, uint32_t *watch, uint32_t code, uint32_t x, uint32_t y) {
+    if (ptx::mbar_try_wait(bar, parity)) return true;
+    watchdog dog(watch);
+    while (!ptx::mbar_try_wait(bar, parity)) {
+        if (dog.expired(code, x, y, parity)) return false;
+    }
+    return true;
 }
 
 // ---- cube input ------------------------------------------------------------------------------------
@@ -387,6 +453,338 @@ __global__ void __launch_bounds__(kCubeThreads)
         prev_t = t;
         prev_words = cube_words;
         prev_slot = s;
+    }
+}
+
+// =====================================================================================================
+// compress, warp-specialised (the default for TMA-compatible inputs)
+// =====================================================================================================
+//
+// One persistent CTA per SM owns ALL of the SM's shared memory as a ring of S cube slots and splits its
+// warps by role, so that the warps doing the integer work never wait for anything but their input tile:
+//
+//   loader  (1 warp, 1 lane)  draws tickets (ticket order == cube order), waits for a free slot and issues
+//                             the TMA tensor load of the cube into it                      -> full[s]
+//   encoder (G groups of 4 warps; group g takes the CTA's cubes g, g+G, ...)
+//                             full[s] -> residuals, heads, plane counts -> named barrier of the group ->
+//                             publish the cube length -> transpose + compaction into the cube image, in
+//                             place over the input tile                                     -> done[s]
+//   retire  (R warps; warp r takes cubes r, r+R, ...)
+//                             done[s] -> decoupled look-back -> header entry -> coalesced copy of the image
+//                             from the slot to its final stream position                   -> empty[s]
+//
+// Against compress_kernel (3 slots per 4 warps, everything done by the same 4 warps): the pooled ring
+// feeds 6 instead of 4 encoder groups per SM from the same shared memory, and the look-back latency and
+// the copy-out land on warps that have nothing else to do.
+//
+// The copy-out is done by the retire warp's own loads and stores because a cube's destination is only
+// 4-byte aligned (the stream format packs cubes word by word): cp.async.bulk needs 16-byte alignment, and
+// TMA tensor stores turned out to need it too — cp.async.bulk.tensor.{1d,2d}.global.shared::cta with an
+// element coordinate that is not a multiple of 16 bytes (or is negative) raises "illegal instruction" on
+// sm_100a, while the same box at an aligned coordinate stores correctly (scripts/ubench/tma_store_probe.cu,
+// results in profiles/README.md).
+//
+// Deadlock freedom: a ticket is only drawn for a slot that is free, its TMA load is issued at once, and
+// the groups take the CTA's cubes in ticket order; publishing a cube's length therefore never depends on
+// a later ticket, and a look-back only waits for the lengths of earlier tickets.
+
+constexpr uint32_t kNoTicket = 0xffffffffu;
+
+template<typename Bits>
+struct ws_plan {
+    static constexpr int slot_bytes = smem_plan<Bits>::slot_bytes;
+    static constexpr int aux_bytes = 2048;
+    static constexpr int slots = (232448 - aux_bytes) / slot_bytes;  // 227 KiB of dynamic shared memory per CTA
+};
+
+template<int S, int G>
+struct ws_aux {
+    uint64_t full[S], done[S], empty[S], taken[S];
+    uint32_t ticket[S];
+    uint32_t seq[S];    // which of the CTA's cubes the slot holds (guards against mbarrier phase-parity aliasing)
+    uint32_t words[S];
+    uint32_t warp_total[2][G][4];
+};
+
+template<typename Bits>
+constexpr size_t ws_smem_bytes() {
+    return static_cast<size_t>(ws_plan<Bits>::slots) * ws_plan<Bits>::slot_bytes + ws_plan<Bits>::aux_bytes;
+}
+
+template<typename Bits, int Dims, int G, int R, int LB, int LA, int PF, bool Stats>
+__global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
+        compress_ws_kernel(const compress_launch a, const __grid_constant__ CUtensorMap in_map) {
+    using tr = codec_traits<Bits>;
+    constexpr int S = ws_plan<Bits>::slots;
+    constexpr int slot_words = ws_plan<Bits>::slot_bytes / 4;
+    constexpr uint32_t kPoison = G > R ? G : R;  // end markers: one for every group and every retire warp
+    static_assert(S > G && S > R && S >= static_cast<int>(kPoison), "ring too small");
+    static_assert(sizeof(ws_aux<S, G>) <= ws_plan<Bits>::aux_bytes, "aux area too small");
+    static_assert(PF < S, "prefetch limit must be below the ring size");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint32_t *slots = reinterpret_cast<uint32_t *>(smem_raw);
+    auto &aux = *reinterpret_cast<ws_aux<S, G> *>(smem_raw + S * ws_plan<Bits>::slot_bytes);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            ptx::mbar_init(&aux.full[s], 1);
+            ptx::mbar_init(&aux.done[s], kCubeThreads);
+            ptx::mbar_init(&aux.empty[s], 1);
+            ptx::mbar_init(&aux.taken[s], 1);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();  // the only CTA-wide barrier; the roles below never meet again
+    // Stats instantiations only (tuning runs): cycles spent per role and wait, summed over the grid into a.stats
+    long long st_a = 0, st_b = 0, st_c = 0;
+    uint32_t st_n = 0, st_polls = 0;
+    auto now = [] { return Stats ? clock64() : 0ll; };
+
+    if (warp < 4 * G) {
+        // ---------------------------------------------------------------------------------- encoder
+        const int g = warp >> 2, u = tid & (kCubeThreads - 1), wg = warp & 3;
+        int s = g;
+        uint32_t parity = 0, flip = 0, seq = g;
+        for (;; seq += G) {
+            // A parity wait cannot tell "phase r completed" from "phase r-1 still running": when the TMA load of
+            // the cube one ring round back is slower than this group (seen on 1-D inputs, about once in 10^5
+            // cubes), the wait falls through while the slot still belongs to that cube. The slot's sequence
+            // tag, written by the loader before it arms the barrier, tells the two apart.
+            bool alive = true;
+            const long long c0 = now();
+            do {
+                alive = mbar_wait_watched(&aux.full[s], parity, a.watch, 0xF011u, static_cast<uint32_t>(s), (seq << 8) | static_cast<uint32_t>(warp));
+            } while (alive && *reinterpret_cast<volatile uint32_t *>(&aux.seq[s]) != seq);
+            const long long c1 = now();
+            st_a += c1 - c0;
+            if (PF > 0 && u == 0) ptx::mbar_arrive(&aux.taken[s]);  // lets the loader go PF cubes ahead of the encoders, no further
+            if (!alive) {
+                // watchdog: release siblings that may already stand at the group's barrier, then leave
+                asm volatile("bar.arrive %0, %1;" ::"r"(1 + g), "r"(kCubeThreads) : "memory");
+                break;
+            }
+            const uint32_t t = aux.ticket[s];
+            if (t >= a.count) {
+                // end marker number kNoTicket - t: hand it on to the retire warps; leave with the last one
+                // that is addressed to this group
+                ptx::mbar_arrive(&aux.done[s]);
+                if ((kNoTicket - t) + G >= kPoison) break;
+                s += G;
+                if (s >= S) {
+                    s -= S;
+                    parity ^= 1u;
+                }
+                continue;
+            }
+            uint32_t *tile = slots + s * slot_words;
+
+            // phase 1: residuals of run u, chunk head, plane count
+            Bits r[32];
+            residual_run<Bits, Dims>(tile, u, r);
+            Bits head = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) head |= r[j];
+            uint32_t count;
+            if constexpr (sizeof(Bits) == 4) {
+                count = popc_bits(head);
+            } else {
+                head |= __shfl_xor_sync(kFullMask, head, 1);  // chunk = two adjacent runs
+                count = (u & 1) == 0 ? popc_bits(head) : 0u;
+            }
+            const uint32_t inclusive = warp_inclusive_sum(count, lane);
+            if (lane == 31) aux.warp_total[flip][g][wg] = inclusive;
+            ptx::named_barrier(1 + g, kCubeThreads);  // reads of the input tile done; warp totals visible
+
+            uint32_t before = 0, cube_words = tr::chunks;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t wt = aux.warp_total[flip][g][w];
+                cube_words += wt;
+                if (w < wg) before += wt;
+            }
+            flip ^= 1u;
+            uint32_t body = tr::chunks + before + inclusive - count;
+            if constexpr (sizeof(Bits) == 8) body = __shfl_sync(kFullMask, body, lane & ~1);
+            if (u == 0) {
+                ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, kStatusAggregate, cube_words));
+                aux.words[s] = cube_words;
+            }
+            const long long c2 = now();
+            st_b += c2 - c1;
+
+            // phase 2: bit planes, compacted into the cube image (in place over the input tile)
+            if constexpr (sizeof(Bits) == 4) {
+                uint32_t planes[32];
+                planes_of_run(r, planes);
+                compact_planes(tile, u, head, body, planes);
+            } else {
+                uint32_t planes_hi[32], planes_lo[32];
+                planes_of_run(r, planes_hi, planes_lo);
+                compact_planes(tile, u >> 1, (u & 1) == 0, head, body, planes_hi, planes_lo);
+            }
+            ptx::mbar_arrive(&aux.done[s]);
+            st_c += now() - c2;
+            ++st_n;
+
+            s += G;
+            if (s >= S) {
+                s -= S;
+                parity ^= 1u;
+            }
+        }
+        if (Stats && a.stats && (tid & 127) == 0) {
+            atomicAdd(a.stats + 0, static_cast<unsigned long long>(st_a));   // encoder: waiting for the input tile
+            atomicAdd(a.stats + 1, static_cast<unsigned long long>(st_b));   // encoder: phase 1 (to the published length)
+            atomicAdd(a.stats + 2, static_cast<unsigned long long>(st_c));   // encoder: phase 2
+            atomicAdd(a.stats + 3, static_cast<unsigned long long>(st_n));   // cubes
+        }
+    } else if (warp == 4 * G) {
+        // ----------------------------------------------------------------------------------- loader
+        if (lane != 0) return;
+        ptx::tma_prefetch_desc(&in_map);
+        // Tickets are drawn LA cubes ahead and kept in registers, so the ~1 us round trip of
+        // the atomic is never waited for (a ticket drawn early still only ever waits for EARLIER tickets:
+        // for the slot of the CTA's cube S places back, whose retirement needs lengths of earlier cubes).
+        uint32_t tk[LA];
+        {
+            const uint32_t first = atomicAdd(a.ticket, static_cast<uint32_t>(LA)) - a.ticket_base;
+#pragma unroll
+            for (int j = 0; j < LA; ++j) tk[j] = first + j;
+        }
+        int s = 0;
+        uint32_t parity = 1;  // parity of the phase of empty[s] that ends the PREVIOUS round (none in round 0)
+        bool first_round = true;
+        uint32_t poison = 0, seq = 0;
+        int ts = 0;            // slot / parity of the cube PF places back
+        uint32_t tparity = 0;
+        const long long l0 = now();
+        while (poison < kPoison) {
+#pragma unroll
+            for (int j = 0; j < LA; ++j) {
+                if (poison == kPoison) break;
+                const long long c0 = now();
+                if (!first_round && !mbar_wait_watched(&aux.empty[s], parity, a.watch, 0xE017u, static_cast<uint32_t>(s), seq)) return;
+                const long long c1 = now();
+                st_a += c1 - c0;
+                if (PF > 0 && seq >= static_cast<uint32_t>(PF)) {
+                    // just-in-time loading: cube seq-PF must have been started by its encoder group
+                    if (!mbar_wait_watched(&aux.taken[ts], tparity, a.watch, 0x7A4Eu, static_cast<uint32_t>(ts), seq)) return;
+                    if (++ts == S) {
+                        ts = 0;
+                        tparity ^= 1u;
+                    }
+                }
+                st_b += now() - c1;
+                const uint32_t t = tk[j];
+                if (t < a.count) {
+                    tk[j] = atomicAdd(a.ticket, 1u) - a.ticket_base;
+                    aux.ticket[s] = t;
+                    aux.seq[s] = seq;
+                    ptx::fence_proxy_async_smem();  // the slot's previous life (generic reads/writes) before the TMA write
+                    issue_tma_load<Bits, Dims>(slots + s * slot_words, &aux.full[s], &in_map, a.geom, a.hc_begin + t);
+                } else {
+                    aux.ticket[s] = kNoTicket - poison;  // end marker number `poison`
+                    aux.seq[s] = seq;
+                    ptx::mbar_arrive(&aux.full[s]);
+                    ++poison;
+                }
+                ++seq;
+                if (++s == S) {
+                    s = 0;
+                    parity ^= 1u;
+                    first_round = false;
+                }
+            }
+        }
+        if (Stats && a.stats) {
+            atomicAdd(a.stats + 4, static_cast<unsigned long long>(st_a));          // loader: waiting for a free slot
+            atomicAdd(a.stats + 5, static_cast<unsigned long long>(st_b));          // loader: waiting for the encoders (prefetch limit)
+            atomicAdd(a.stats + 6, static_cast<unsigned long long>(now() - l0));    // loader: total
+        }
+    } else {
+        // ----------------------------------------------------------------------------------- retire
+        const int rw = warp - (4 * G + 1);
+        const uint32_t launch_base = a.base_words ? *a.base_words : 0u;
+        Bits *out_cubes = static_cast<Bits *>(a.out_cubes);
+        int s = rw;
+        uint32_t parity = 0, seq = rw;
+        for (;; seq += R) {
+            bool alive = true;
+            const long long c0 = now();
+            do {  // same aliasing guard as in the encoder
+                alive = mbar_wait_watched(&aux.done[s], parity, a.watch, 0xD01Eu, static_cast<uint32_t>(s), (seq << 8) | static_cast<uint32_t>(warp));
+            } while (alive && *reinterpret_cast<volatile uint32_t *>(&aux.seq[s]) != seq);
+            if (!alive) break;
+            const long long c1 = now();
+            st_a += c1 - c0;
+            const uint32_t t = aux.ticket[s];
+            if (t >= a.count) {
+                if ((kNoTicket - t) + R >= kPoison) break;  // the last end marker addressed to this warp
+                s += R;
+                if (s >= S) {
+                    s -= S;
+                    parity ^= 1u;
+                }
+                continue;
+            }
+            const uint32_t words = aux.words[s];
+            uint32_t exclusive = launch_base;
+            if (a.debug_flags & 2u) {
+                exclusive = t * static_cast<uint32_t>(tr::max_cube_words);  // profiling aid: no look-back, fixed-stride output (NOT the stream format)
+            } else if (t != 0) {
+                const look_back_window<LB> first = look_back_load<LB>(a.desc, static_cast<int64_t>(t) - 1, a.epoch, lane, launch_base);
+                bool aborted = false;
+                exclusive = look_back<LB>(a.desc, t, a.epoch, lane, first, launch_base, a.watch, &aborted, Stats ? &st_polls : nullptr);
+                if (aborted) break;
+            }
+            const long long c2 = now();
+            st_b += c2 - c1;
+            if (lane == 0) {
+                const uint32_t after = exclusive + words;
+                ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, kStatusPrefix, after));
+                a.out_offsets[t] = after;  // "offset_after", reference src/ndzip/common.hh:342-347
+                if (t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452
+                if (t == a.count - 1) {
+                    *a.total_words = after;
+                    if (a.length_out) *a.length_out = a.length_add + after;  // cuda_codec.inl:507-511
+                }
+            }
+            // image -> stream, coalesced (whole words of the stream: 4 bytes float, 8 bytes double)
+            if (!(a.debug_flags & 1u)) {  // (profiling aid: bit 0 skips the copy)
+                const Bits *src = reinterpret_cast<const Bits *>(slots + s * slot_words);
+                Bits *dst = out_cubes + exclusive;
+                uint32_t w = lane;
+                for (; w + 96 < words; w += 128) {
+                    const Bits v0 = src[w], v1 = src[w + 32], v2 = src[w + 64], v3 = src[w + 96];
+                    dst[w] = v0;
+                    dst[w + 32] = v1;
+                    dst[w + 64] = v2;
+                    dst[w + 96] = v3;
+                }
+                for (; w < words; w += 32) dst[w] = src[w];
+            }
+            ptx::fence_proxy_async_smem();   // these generic reads before the next TMA load into the slot
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&aux.empty[s]);
+            st_c += now() - c2;
+            ++st_n;
+
+            s += R;
+            if (s >= S) {
+                s -= S;
+                parity ^= 1u;
+            }
+        }
+        if (Stats && a.stats && lane == 0) {
+            atomicAdd(a.stats + 8, static_cast<unsigned long long>(st_a));     // retire: waiting for an encoded cube
+            atomicAdd(a.stats + 9, static_cast<unsigned long long>(st_b));     // retire: look-back
+            atomicAdd(a.stats + 10, static_cast<unsigned long long>(st_c));    // retire: header entry + copy-out
+            atomicAdd(a.stats + 11, static_cast<unsigned long long>(st_n));    // cubes
+            atomicAdd(a.stats + 12, static_cast<unsigned long long>(st_polls & 0xffffu));   // look-back: reloads because a predecessor's length was missing
+            atomicAdd(a.stats + 13, static_cast<unsigned long long>(st_polls >> 16));       // look-back: windows beyond the first
+        }
     }
 }
 
@@ -728,6 +1126,62 @@ decompress_fn decompress_entry(int dtype, int dims, bool vec) {
     return dims == 1 ? decompress_for<uint64_t, 1>(vec) : dims == 2 ? decompress_for<uint64_t, 2>(vec) : decompress_for<uint64_t, 3>(vec);
 }
 
+using compress_ws_fn = void (*)(const compress_launch, const CUtensorMap);
+
+// (encoder groups, retire warps) per CTA; variant 0 is the default, the others exist for tuning runs
+// (NDZB_WS_VARIANT) and are documented with their measurements in profiles/README.md
+struct ws_variant {
+    int groups, retire, look_back_depth, ticket_lookahead, prefetch_limit;
+    bool stats;
+};
+constexpr ws_variant kWsVariants32[] = {{5, 3, 2, 1, 0, false}, {5, 4, 2, 1, 0, false}, {5, 5, 2, 1, 0, false}, {5, 6, 2, 1, 0, false},
+        {4, 4, 2, 1, 0, false}, {4, 5, 2, 1, 0, false}, {4, 6, 2, 1, 0, false}, {5, 5, 2, 1, 0, true}};
+constexpr ws_variant kWsVariants64[] = {{3, 2, 2, 1, 0, false}, {3, 3, 2, 1, 0, false}, {3, 4, 2, 1, 0, false}, {2, 3, 2, 1, 0, false}, {3, 3, 2, 1, 0, true}};
+constexpr int kNumWsVariants32 = sizeof(kWsVariants32) / sizeof(ws_variant);
+constexpr int kNumWsVariants64 = sizeof(kWsVariants64) / sizeof(ws_variant);
+
+template<typename Bits, int Dims, int V>
+compress_ws_fn compress_ws_variant_fn() {
+    if constexpr (sizeof(Bits) == 4) {
+        constexpr ws_variant v = kWsVariants32[V];
+        return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.prefetch_limit, v.stats>;
+    } else {
+        constexpr ws_variant v = kWsVariants64[V];
+        return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.prefetch_limit, v.stats>;
+    }
+}
+
+template<typename Bits, int Dims>
+compress_ws_fn compress_ws_for(int variant) {
+    if constexpr (sizeof(Bits) == 4) {
+        switch (variant) {
+            case 1: return compress_ws_variant_fn<Bits, Dims, 1>();
+            case 2: return compress_ws_variant_fn<Bits, Dims, 2>();
+            case 3: return compress_ws_variant_fn<Bits, Dims, 3>();
+            case 4: return compress_ws_variant_fn<Bits, Dims, 4>();
+            case 5: return compress_ws_variant_fn<Bits, Dims, 5>();
+            case 6: return compress_ws_variant_fn<Bits, Dims, 6>();
+            case 7: return compress_ws_variant_fn<Bits, Dims, 7>();
+            default: return compress_ws_variant_fn<Bits, Dims, 0>();
+        }
+    } else {
+        switch (variant) {
+            case 1: return compress_ws_variant_fn<Bits, Dims, 1>();
+            case 2: return compress_ws_variant_fn<Bits, Dims, 2>();
+            case 3: return compress_ws_variant_fn<Bits, Dims, 3>();
+            case 4: return compress_ws_variant_fn<Bits, Dims, 4>();
+            default: return compress_ws_variant_fn<Bits, Dims, 0>();
+        }
+    }
+}
+compress_ws_fn compress_ws_entry(int dtype, int dims, int variant) {
+    if (dtype == 0) {
+        return dims == 1 ? compress_ws_for<uint32_t, 1>(variant) : dims == 2 ? compress_ws_for<uint32_t, 2>(variant) : compress_ws_for<uint32_t, 3>(variant);
+    }
+    return dims == 1 ? compress_ws_for<uint64_t, 1>(variant) : dims == 2 ? compress_ws_for<uint64_t, 2>(variant) : compress_ws_for<uint64_t, 3>(variant);
+}
+size_t compress_ws_smem(int dtype) { return dtype == 0 ? ws_smem_bytes<uint32_t>() : ws_smem_bytes<uint64_t>(); }
+
 size_t compress_smem(int dtype) { return dtype == 0 ? compress_smem_bytes<uint32_t>() : compress_smem_bytes<uint64_t>(); }
 size_t decompress_smem(int dtype) { return dtype == 0 ? decompress_smem_bytes<uint32_t>() : decompress_smem_bytes<uint64_t>(); }
 
@@ -740,6 +1194,13 @@ size_t decompress_smem(int dtype) { return dtype == 0 ? decompress_smem_bytes<ui
 uint32_t compress_ticket_overdraw(uint32_t grid) {
     return grid;  // every CTA draws one ticket up front and one more per cube it processes
 }
+int compress_ws_variants(int dtype);
+uint32_t compress_ws_ticket_overdraw(int dtype, int variant, uint32_t grid) {
+    if (variant < 0 || variant >= compress_ws_variants(dtype)) variant = 0;
+    const ws_variant v = dtype == 0 ? kWsVariants32[variant] : kWsVariants64[variant];
+    return grid * static_cast<uint32_t>(v.ticket_lookahead);  // the loader draws that many up front, then one per cube
+}
+int compress_ws_variants(int dtype) { return dtype == 0 ? kNumWsVariants32 : kNumWsVariants64; }
 
 cudaError_t configure_kernels(kernel_config &cfg) {
     int dev = 0;
@@ -755,6 +1216,11 @@ cudaError_t configure_kernels(kernel_config &cfg) {
                 if (err != cudaSuccess) return err;
                 err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                         &cfg.ctas_per_sm[dtype][dims - 1][p], fn, kCubeThreads, compress_smem(dtype));
+                if (err != cudaSuccess) return err;
+            }
+            for (int v = 0; v < compress_ws_variants(dtype); ++v) {
+                err = cudaFuncSetAttribute(compress_ws_entry(dtype, dims, v), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        static_cast<int>(compress_ws_smem(dtype)));
                 if (err != cudaSuccess) return err;
             }
             for (int v = 0; v < 2; ++v) {
@@ -774,6 +1240,15 @@ cudaError_t launch_compress(int dtype, int dims, load_path path, const compress_
         uint32_t grid, cudaStream_t stream) {
     static const CUtensorMap dummy{};
     compress_entry(dtype, dims, path)<<<grid, kCubeThreads, compress_smem(dtype), stream>>>(args, tmap ? *tmap : dummy);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compress_ws(int dtype, int dims, int variant, const compress_launch &args, const CUtensorMap &in_map,
+        uint32_t grid, cudaStream_t stream) {
+    if (variant < 0 || variant >= compress_ws_variants(dtype)) variant = 0;
+    const ws_variant v = dtype == 0 ? kWsVariants32[variant] : kWsVariants64[variant];
+    const uint32_t threads = static_cast<uint32_t>(4 * v.groups + 1 + v.retire) * 32u;
+    compress_ws_entry(dtype, dims, variant)<<<grid, threads, compress_ws_smem(dtype), stream>>>(args, in_map);
     return cudaGetLastError();
 }
 

@@ -14,6 +14,8 @@ enum class load_path : int {
     scalar = 2,  // element-wise global loads: any shape / alignment
 };
 
+constexpr uint32_t kWatchdogWords = 8 + 6 * 4000;
+
 struct compress_launch {
     const void *data;          // element 0 of the (global) array
     grid_geom geom;
@@ -30,6 +32,9 @@ struct compress_launch {
     uint32_t *ticket;          // free-running ticket counter
     uint32_t ticket_base;      // value of *ticket when this launch starts
     uint32_t epoch;            // tag that invalidates descriptors of earlier launches (< 2^30)
+    uint32_t debug_flags;      // compress_ws_kernel profiling aids (NDZB_WS_DEBUG): 1 = skip the copy-out, 2 = skip the look-back
+    unsigned long long *stats; // compress_ws_kernel, Stats instantiations: 16 counters summed over the grid (nullable)
+    uint32_t *watch;           // compress_ws_kernel: kWatchdogWords words, spin-loop watchdog ([0] raised flag, [1] records, [7] 1 = no trap, [8..] records)
 };
 
 struct decompress_launch {
@@ -54,6 +59,11 @@ uint32_t compress_ticket_overdraw(uint32_t grid);
 
 // All launchers are asynchronous on `stream` and return the launch error, if any.
 cudaError_t launch_compress(int dtype, int dims, load_path path, const compress_launch &args, const CUtensorMap *tmap,
+        uint32_t grid, cudaStream_t stream);
+// Warp-specialised compress kernel (TMA-compatible inputs only): one CTA per SM, `variant` < compress_ws_variants(dtype).
+uint32_t compress_ws_ticket_overdraw(int dtype, int variant, uint32_t grid);
+int compress_ws_variants(int dtype);
+cudaError_t launch_compress_ws(int dtype, int dims, int variant, const compress_launch &args, const CUtensorMap &in_map,
         uint32_t grid, cudaStream_t stream);
 cudaError_t launch_decompress(int dtype, int dims, bool vec_store, const decompress_launch &args, uint32_t grid,
         cudaStream_t stream);

@@ -39,6 +39,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// named barrier among `threads` threads of the CTA (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // generic-proxy accesses to shared memory (our LDS/STS) must be ordered before a later async-proxy
 // write (the next TMA load into the same slot)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -24,6 +24,26 @@ def load_path(name):
             os.environ["NDZB_LOAD_PATH"] = old
 
 
+@contextmanager
+def compress_kernel(kind=None, variant=None):
+    """Select the compress kernel for TMA-compatible inputs (read by ndzb_ctx_create):
+    kind "v1" = compress_kernel, anything else = compress_ws_kernel in tuning variant `variant`."""
+    saved = {k: os.environ.get(k) for k in ("NDZB_COMPRESS_KERNEL", "NDZB_WS_VARIANT")}
+    for k, v in (("NDZB_COMPRESS_KERNEL", kind), ("NDZB_WS_VARIANT", None if variant is None else str(variant))):
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+    try:
+        yield
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def _torch_bits(dtype):
     import torch
     return torch.int32 if np.dtype(dtype) == np.float32 else torch.int64

@@ -110,6 +110,55 @@ def test_aligned_multi_cube_equals_reference(nz, oracle, dtype, dims):
     assert gpu_decompress(stream, dtype, shape).tobytes() == data.tobytes()
 
 
+# (kernel, variant): compress_kernel ("v1") and every tuning variant of the warp-specialised kernel
+KERNELS = [("v1", None)] + [("ws", v) for v in range(8)]
+
+
+@pytest.mark.parametrize("kernel,variant", KERNELS, ids=[k if v is None else f"{k}{v}" for k, v in KERNELS])
+@pytest.mark.parametrize("gen", ["hashed", "smooth", "zeros"])
+@pytest.mark.parametrize("dtype,dims", PROFILES)
+def test_tma_compatible_bordered_shapes_all_kernels(nz, oracle, dtype, dims, gen, kernel, variant):
+    # bordered shapes whose row pitch is still 16-byte aligned, so the TMA input path (and with it the
+    # warp-specialised kernel) is taken: incompressible cubes (longest images), smooth data, and all-zero
+    # cubes (shortest images: heads only)
+    from gpu_util import gpu_compress, gpu_decompress, compress_kernel
+    if kernel == "ws" and variant >= (8 if dtype == "float32" else 5):
+        pytest.skip("no such variant for this data type")
+    shape = {1: (9 * 4096 + 123,), 2: (200, 260), 3: (40, 52, 68)}[dims]
+    data = np.zeros(shape, dtype) if gen == "zeros" else synth.make(gen, shape, dtype, seed=11)
+    expect = oracle.compress(data)
+    with compress_kernel(kernel, variant):
+        stream, _ = gpu_compress(data)
+    assert stream.size == expect.size
+    assert np.array_equal(stream, expect)
+    assert gpu_decompress(stream, dtype, shape).tobytes() == data.tobytes()
+
+
+@pytest.mark.parametrize("kernel", ["v1", "ws"])
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_many_incompressible_cubes_and_misaligned_stream_pointer(nz, oracle, dtype, kernel):
+    # several cubes per encoder group and SM, all of maximum length; the stream buffer starts one word
+    # into an allocation, so neither the header nor the cubes are 16-byte aligned
+    import torch
+    from gpu_util import to_device, compress_kernel
+    shape = (560 * 4096,) if dtype == "float32" else (300 * 4096,)
+    data = synth.make("hashed", shape, dtype, seed=3)
+    expect = oracle.compress(data)
+    tbits = torch.int32 if dtype == "float32" else torch.int64
+    with compress_kernel(kernel, None):
+        comp = nz.make_cuda_compressor(dtype, nz.compressor_requirements(shape))
+        backing = torch.zeros(nz.compressed_length_bound(dtype, shape) + 1, dtype=tbits, device="cuda")
+        d_stream = backing[1:]
+        d_len = torch.zeros(1, dtype=torch.int32, device="cuda")
+        comp.compress(to_device(data), shape, d_stream, d_len)
+        torch.cuda.synchronize()
+    n = int(d_len.cpu().numpy().view(np.uint32)[0])
+    assert n == expect.size
+    got = d_stream[:n].cpu().numpy().view(expect.dtype)
+    assert np.array_equal(got, expect)
+    assert int(backing[0].item()) == 0
+
+
 @pytest.mark.parametrize("dtype,dims", PROFILES)
 @pytest.mark.parametrize("n", [0, 1])
 def test_zero_hypercube_extents(nz, oracle, dtype, dims, n):
