@@ -12,7 +12,7 @@ A "step" is one pass of the hot path (compress, offset exchange, decompress) ove
 Inputs (512 MiB per rank) are larger than the 126 MB L2, so no explicit L2 flush is needed.
 
 One JSON line on stdout (rank 0). Keys beyond the base contract:
-  roofline     dominant kernel (compress_kernel): algorithmic bytes (input + stream) / CUDA-event time
+  roofline     dominant kernel (compress_ws_kernel): algorithmic bytes (input + stream) / CUDA-event time
                of that launch alone, against MEASURED_PEAKS.json's hbm_gbs.
   cpu_baseline the UNMODIFIED reference CPU codec (oracle/_ref, OpenMP, all host threads) on a bounded
                sample of the same grid.
@@ -502,7 +502,7 @@ def main():
         },
         "compress_gbs": nbytes_rank / (tc_avg * 1e-3) / 1e9, "decompress_gbs": nbytes_rank / (td_avg * 1e-3) / 1e9,
         "compress_ms": tc_avg, "decompress_ms": td_avg, "compress_ms_min": min(tc), "decompress_ms_min": min(td),
-        "roofline": {"bound": "hbm", "kernel": "compress_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "compress_ws_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes": algo_bytes,
                      "traffic": ncu_traffic_per_launch(args.workload),
                      "decompress_kernel": {"achieved": dec_achieved, "frac": dec_achieved / peak}},

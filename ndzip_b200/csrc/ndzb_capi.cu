@@ -199,8 +199,9 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
             NDZB_CUDA(cudaMemset(ctx->d_stats, 0, sizeof h));
             const double enc = h[3] ? double(h[3]) : 1.0, ret = h[11] ? double(h[11]) : 1.0, g = grid;
             fprintf(stderr, "ws stats (cycles per cube) enc: wait_tile %.0f phase1 %.0f phase2 %.0f | loader per cube: wait_slot %.0f wait_encoders %.0f total %.0f | "
-                    "retire: wait_cube %.0f look_back %.0f copy %.0f polls/cube %.2f extra_windows/cube %.2f\n",
-                    h[0] / enc, h[1] / enc, h[2] / enc, h[4] / ret, h[5] / ret, h[6] / ret, h[8] / ret, h[9] / ret, h[10] / ret, h[12] / ret, h[13] / ret);
+                    "retire: wait_cube %.0f look_back %.0f wait_image %.0f copy %.0f polls/cube %.2f extra_windows/cube %.2f\n",
+                    h[0] / enc, h[1] / enc, h[2] / enc, h[4] / ret, h[5] / ret, h[6] / ret, h[8] / ret, h[9] / ret, h[14] / ret, h[10] / ret, h[12] / ret, h[13] / ret);
+            fprintf(stderr, "ws stats (cycles per cube) slot: freed->load issued %.0f, load issued->encoder starts %.0f\n", h[15] / ret, h[7] / enc);
             (void) g;
         }
         if (ctx->ws_check) {

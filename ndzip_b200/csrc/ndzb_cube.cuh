@@ -495,6 +495,61 @@ template<> NDZB_HD void tile_store<uint64_t>(uint32_t *tile, int e, uint64_t v) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// inverse: strip addresses of the column passes
+//
+// The y / z prefix-sum passes of the decoder walk two-element strips (2 consecutive x) down a column.
+// tile_elem() of every strip costs ~5 integer instructions (the swizzle XOR depends on the row), which
+// made address arithmetic ~12 % of the decoder. Along a column the XOR term only takes a few values
+// that are known at compile time once the loop is unrolled, so the run-time part is folded into a few
+// base registers and everything else into the load/store immediate:  address(k) = base[sel(k)] + imm(k).
+// tests/host_sim checks every address against tile_elem().
+
+// 3-D, y pass: strip (z = o, y = k, x = 2 xq)
+template<typename Bits>
+struct strip_addr_y3 {
+    static constexpr int kBases = sizeof(Bits) == 4 ? 4 : 8;
+    int base[kBases];
+    NDZB_HD strip_addr_y3(int o, int xq) {
+#pragma unroll
+        for (int m = 0; m < kBases; ++m) {
+            if constexpr (sizeof(Bits) == 4) base[m] = o * 256 + (((xq >> 1) ^ m) << 2) + ((xq & 1) << 1);
+            else base[m] = o * 256 + ((xq ^ m) << 2);
+        }
+    }
+    NDZB_HD int at(int k) const {
+        const int c = k >> 1;
+        if constexpr (sizeof(Bits) == 4) return base[c & 3] + c * 32 + ((((k & 1) * 4) ^ (c & 4)) << 2);
+        else return base[c] + (k & 1) * 4096 + c * 32;
+    }
+};
+
+// 3-D, z pass: strip (z = k, y = o, x = 2 xq) — the swizzle does not depend on z
+template<typename Bits>
+struct strip_addr_z3 {
+    int base;
+    NDZB_HD strip_addr_z3(int o, int xq) : base(tile_elem<Bits>(o * 16 + xq * 2)) {}
+    NDZB_HD int at(int k) const { return base + k * 256; }
+};
+
+// 2-D, y pass: strip (y = 16 seg + k, x = 2 xq), xq < 32
+template<typename Bits>
+struct strip_addr_y2 {
+    int base[4];
+    NDZB_HD strip_addr_y2(int seg, int xq) {
+        const int hb = xq >> 4;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            if constexpr (sizeof(Bits) == 4) {
+                base[m] = seg * 1024 + hb * 32 + (((((xq & 15) >> 1) ^ hb) ^ (2 * m)) << 2) + ((xq & 1) << 1);
+            } else {
+                base[m] = ((xq >> 3) & 1) * 4096 + seg * 1024 + hb * 32 + ((((xq & 7) ^ hb) ^ (2 * m)) << 2);
+            }
+        }
+    }
+    NDZB_HD int at(int k) const { return base[k & 3] + k * 64; }
+};
+
+// ------------------------------------------------------------------------------------------------
 // geometry shared by kernels and host code
 
 // Exact unsigned division by a launch-invariant divisor without the ~20-instruction hardware

@@ -499,10 +499,12 @@ struct ws_plan {
 
 template<int S, int G>
 struct ws_aux {
-    uint64_t full[S], done[S], empty[S], taken[S];
+    uint64_t full[S], done[S], empty[S], taken[S], counted[S];
     uint32_t ticket[S];
     uint32_t seq[S];    // which of the CTA's cubes the slot holds (guards against mbarrier phase-parity aliasing)
     uint32_t words[S];
+    uint32_t issued[S];  // Stats instantiations: clock (low word) at which the slot's TMA load was issued
+    uint32_t freed[S];   //                       clock at which the slot was handed back to the loader
     uint32_t warp_total[2][G][4];
 };
 
@@ -511,7 +513,55 @@ constexpr size_t ws_smem_bytes() {
     return static_cast<size_t>(ws_plan<Bits>::slots) * ws_plan<Bits>::slot_bytes + ws_plan<Bits>::aux_bytes;
 }
 
-template<typename Bits, int Dims, int G, int R, int LB, int LA, int PF, bool Stats>
+// Cube image (shared memory, 1024-byte aligned) -> its place in the stream, by one warp. The destination is only
+// 4-byte aligned; the words up to the first 16-byte boundary and the last < 4 words are stored one by one, the
+// body as aligned 16-byte stores whose four words are picked from two aligned 16-byte shared-memory loads
+// (0.75 instructions per word instead of 2 for a word-by-word copy).
+__device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *dst, uint32_t n, int lane) {
+    const uint32_t head = (4u - ((static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst)) >> 2) & 3u)) & 3u;
+    if (n < head + 4u) {
+        for (uint32_t w = lane; w < n; w += 32) dst[w] = img[w];
+        return;
+    }
+    if (static_cast<uint32_t>(lane) < head) dst[lane] = img[lane];
+    const uint32_t nq = (n - head) >> 2;
+    const quad *sq = reinterpret_cast<const quad *>(img);
+    uint4 *dq = reinterpret_cast<uint4 *>(dst + head);
+    switch (head) {
+        case 0:
+#pragma unroll 4
+            for (uint32_t j = lane; j < nq; j += 32) {
+                const quad a = sq[j];
+                dq[j] = uint4{a.x, a.y, a.z, a.w};
+            }
+            break;
+        case 1:
+#pragma unroll 4
+            for (uint32_t j = lane; j < nq; j += 32) {
+                const quad a = sq[j], b = sq[j + 1];
+                dq[j] = uint4{a.y, a.z, a.w, b.x};
+            }
+            break;
+        case 2:
+#pragma unroll 4
+            for (uint32_t j = lane; j < nq; j += 32) {
+                const quad a = sq[j], b = sq[j + 1];
+                dq[j] = uint4{a.z, a.w, b.x, b.y};
+            }
+            break;
+        default:
+#pragma unroll 4
+            for (uint32_t j = lane; j < nq; j += 32) {
+                const quad a = sq[j], b = sq[j + 1];
+                dq[j] = uint4{a.w, b.x, b.y, b.z};
+            }
+            break;
+    }
+    const uint32_t w = head + (nq << 2) + lane;
+    if (w < n) dst[w] = img[w];
+}
+
+template<typename Bits, int Dims, int G, int R, int LB, int LA, int PF, bool Early, bool Stats>
 __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
         compress_ws_kernel(const compress_launch a, const __grid_constant__ CUtensorMap in_map) {
     using tr = codec_traits<Bits>;
@@ -533,12 +583,13 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             ptx::mbar_init(&aux.done[s], kCubeThreads);
             ptx::mbar_init(&aux.empty[s], 1);
             ptx::mbar_init(&aux.taken[s], 1);
+            ptx::mbar_init(&aux.counted[s], 1);
         }
         ptx::fence_mbar_init();
     }
     __syncthreads();  // the only CTA-wide barrier; the roles below never meet again
     // Stats instantiations only (tuning runs): cycles spent per role and wait, summed over the grid into a.stats
-    long long st_a = 0, st_b = 0, st_c = 0;
+    long long st_a = 0, st_b = 0, st_c = 0, st_d = 0;
     uint32_t st_n = 0, st_polls = 0;
     auto now = [] { return Stats ? clock64() : 0ll; };
 
@@ -559,6 +610,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             } while (alive && *reinterpret_cast<volatile uint32_t *>(&aux.seq[s]) != seq);
             const long long c1 = now();
             st_a += c1 - c0;
+            if (Stats) st_d += static_cast<uint32_t>(static_cast<uint32_t>(c1) - aux.issued[s]);  // TMA issued -> encoder starts
             if (PF > 0 && u == 0) ptx::mbar_arrive(&aux.taken[s]);  // lets the loader go PF cubes ahead of the encoders, no further
             if (!alive) {
                 // watchdog: release siblings that may already stand at the group's barrier, then leave
@@ -569,6 +621,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             if (t >= a.count) {
                 // end marker number kNoTicket - t: hand it on to the retire warps; leave with the last one
                 // that is addressed to this group
+                if (Early && u == 0) ptx::mbar_arrive(&aux.counted[s]);
                 ptx::mbar_arrive(&aux.done[s]);
                 if ((kNoTicket - t) + G >= kPoison) break;
                 s += G;
@@ -610,6 +663,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             if (u == 0) {
                 ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, kStatusAggregate, cube_words));
                 aux.words[s] = cube_words;
+                if (Early) ptx::mbar_arrive(&aux.counted[s]);  // the retire warp resolves the cube's offset while phase 2 runs
             }
             const long long c2 = now();
             st_b += c2 - c1;
@@ -639,6 +693,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             atomicAdd(a.stats + 1, static_cast<unsigned long long>(st_b));   // encoder: phase 1 (to the published length)
             atomicAdd(a.stats + 2, static_cast<unsigned long long>(st_c));   // encoder: phase 2
             atomicAdd(a.stats + 3, static_cast<unsigned long long>(st_n));   // cubes
+            atomicAdd(a.stats + 7, static_cast<unsigned long long>(st_d));   // TMA issue -> encoder start (load latency + waiting for the group)
         }
     } else if (warp == 4 * G) {
         // ----------------------------------------------------------------------------------- loader
@@ -682,6 +737,11 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                     tk[j] = atomicAdd(a.ticket, 1u) - a.ticket_base;
                     aux.ticket[s] = t;
                     aux.seq[s] = seq;
+                    if (Stats) {
+                        const uint32_t c = static_cast<uint32_t>(clock64());
+                        if (!first_round) st_c += static_cast<uint32_t>(c - aux.freed[s]);  // freed -> TMA issued
+                        aux.issued[s] = c;
+                    }
                     ptx::fence_proxy_async_smem();  // the slot's previous life (generic reads/writes) before the TMA write
                     issue_tma_load<Bits, Dims>(slots + s * slot_words, &aux.full[s], &in_map, a.geom, a.hc_begin + t);
                 } else {
@@ -702,6 +762,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             atomicAdd(a.stats + 4, static_cast<unsigned long long>(st_a));          // loader: waiting for a free slot
             atomicAdd(a.stats + 5, static_cast<unsigned long long>(st_b));          // loader: waiting for the encoders (prefetch limit)
             atomicAdd(a.stats + 6, static_cast<unsigned long long>(now() - l0));    // loader: total
+            atomicAdd(a.stats + 15, static_cast<unsigned long long>(st_c));         // slot freed -> its next TMA load issued
         }
     } else {
         // ----------------------------------------------------------------------------------- retire
@@ -714,7 +775,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             bool alive = true;
             const long long c0 = now();
             do {  // same aliasing guard as in the encoder
-                alive = mbar_wait_watched(&aux.done[s], parity, a.watch, 0xD01Eu, static_cast<uint32_t>(s), (seq << 8) | static_cast<uint32_t>(warp));
+                alive = mbar_wait_watched(Early ? &aux.counted[s] : &aux.done[s], parity, a.watch, 0xD01Eu, static_cast<uint32_t>(s), (seq << 8) | static_cast<uint32_t>(warp));
             } while (alive && *reinterpret_cast<volatile uint32_t *>(&aux.seq[s]) != seq);
             if (!alive) break;
             const long long c1 = now();
@@ -751,24 +812,23 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                     if (a.length_out) *a.length_out = a.length_add + after;  // cuda_codec.inl:507-511
                 }
             }
-            // image -> stream, coalesced (whole words of the stream: 4 bytes float, 8 bytes double)
+            long long c3 = c2;
+            if (Early) {
+                // the offset is known; now the image has to be complete (same phase and tag as `counted`)
+                if (!mbar_wait_watched(&aux.done[s], parity, a.watch, 0xD02Eu, static_cast<uint32_t>(s), (seq << 8) | static_cast<uint32_t>(warp))) break;
+                c3 = now();
+                st_d += c3 - c2;
+            }
+            // image -> stream
             if (!(a.debug_flags & 1u)) {  // (profiling aid: bit 0 skips the copy)
-                const Bits *src = reinterpret_cast<const Bits *>(slots + s * slot_words);
-                Bits *dst = out_cubes + exclusive;
-                uint32_t w = lane;
-                for (; w + 96 < words; w += 128) {
-                    const Bits v0 = src[w], v1 = src[w + 32], v2 = src[w + 64], v3 = src[w + 96];
-                    dst[w] = v0;
-                    dst[w + 32] = v1;
-                    dst[w + 64] = v2;
-                    dst[w + 96] = v3;
-                }
-                for (; w < words; w += 32) dst[w] = src[w];
+                constexpr uint32_t w32 = sizeof(Bits) / 4;
+                copy_image_out(slots + s * slot_words, reinterpret_cast<uint32_t *>(out_cubes + exclusive), words * w32, lane);
             }
             ptx::fence_proxy_async_smem();   // these generic reads before the next TMA load into the slot
             __syncwarp();
+            if (Stats && lane == 0) aux.freed[s] = static_cast<uint32_t>(clock64());
             if (lane == 0) ptx::mbar_arrive(&aux.empty[s]);
-            st_c += now() - c2;
+            st_c += now() - c3;
             ++st_n;
 
             s += R;
@@ -784,6 +844,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             atomicAdd(a.stats + 11, static_cast<unsigned long long>(st_n));    // cubes
             atomicAdd(a.stats + 12, static_cast<unsigned long long>(st_polls & 0xffffu));   // look-back: reloads because a predecessor's length was missing
             atomicAdd(a.stats + 13, static_cast<unsigned long long>(st_polls >> 16));       // look-back: windows beyond the first
+            atomicAdd(a.stats + 14, static_cast<unsigned long long>(st_d));    // retire (early look-back): waiting for the image after the offset is known
         }
     }
 }
@@ -798,25 +859,26 @@ template<typename Bits>
 struct strip {
     Bits v[2];
 
-    static __device__ __forceinline__ strip load(const uint32_t *tile, int e) {  // e even
+    // p = tile + word address of the strip (strip_addr_* in ndzb_cube.cuh)
+    static __device__ __forceinline__ strip load(const uint32_t *p) {
         strip s;
         if constexpr (sizeof(Bits) == 4) {
-            const uint2 q = *reinterpret_cast<const uint2 *>(tile + tile_elem<Bits>(e));
+            const uint2 q = *reinterpret_cast<const uint2 *>(p);
             s.v[0] = q.x;
             s.v[1] = q.y;
         } else {
-            const quad q = ld_quad(tile + tile_elem<Bits>(e));
+            const quad q = ld_quad(p);
             s.v[0] = (static_cast<uint64_t>(q.y) << 32) | q.x;
             s.v[1] = (static_cast<uint64_t>(q.w) << 32) | q.z;
         }
         return s;
     }
-    __device__ __forceinline__ void store(uint32_t *tile, int e) const {
+    __device__ __forceinline__ void store(uint32_t *p) const {
         if constexpr (sizeof(Bits) == 4) {
-            *reinterpret_cast<uint2 *>(tile + tile_elem<Bits>(e)) = uint2{v[0], v[1]};
+            *reinterpret_cast<uint2 *>(p) = uint2{v[0], v[1]};
         } else {
-            st_quad(tile + tile_elem<Bits>(e), quad{static_cast<uint32_t>(v[0]), static_cast<uint32_t>(v[0] >> 32),
-                                                     static_cast<uint32_t>(v[1]), static_cast<uint32_t>(v[1] >> 32)});
+            st_quad(p, quad{static_cast<uint32_t>(v[0]), static_cast<uint32_t>(v[0] >> 32), static_cast<uint32_t>(v[1]),
+                            static_cast<uint32_t>(v[1] >> 32)});
         }
     }
     __device__ __forceinline__ strip operator+(const strip &o) const { return strip{{v[0] + o.v[0], v[1] + o.v[1]}}; }
@@ -981,10 +1043,12 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 5 : 3) decom
             __syncthreads();
             constexpr int UE = 16 / sizeof(Bits);
             constexpr int units = kCubeElems / UE;
-#pragma unroll 8
-            for (int q = tid; q < units; q += kCubeThreads) {
-                const int e = q * UE;
-                const quad v = ld_quad(tile + tile_elem<Bits>(e));
+            // unit q = tid + 128 i lies 4 UE runs below unit tid: same swizzle, 128 UE words further
+            const uint32_t *unit0 = tile + tile_elem<Bits>(tid * UE);
+#pragma unroll
+            for (int i = 0; i < units / kCubeThreads; ++i) {
+                const int e = (tid + i * kCubeThreads) * UE;
+                const quad v = ld_quad(unit0 + i * (kCubeThreads * UE));
                 if constexpr (sizeof(Bits) == 4) {
                     const quad o{rotr1(v.x), rotr1(v.y), rotr1(v.z), rotr1(v.w)};
                     if constexpr (Vec16) ptx::stg_stream_v4(data + origin + e, uint4{o.x, o.y, o.z, o.w});
@@ -1001,9 +1065,10 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 5 : 3) decom
             store_run(tile, tid, r);
             __syncthreads();
             const int xq = tid & 31, seg = tid >> 5;
+            const strip_addr_y2<Bits> col(seg, xq);
             S q[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) q[k] = S::load(tile, (seg * 16 + k) * 64 + xq * 2);
+            for (int k = 0; k < 16; ++k) q[k] = S::load(tile + col.at(k));
 #pragma unroll
             for (int k = 1; k < 16; ++k) q[k] = q[k] + q[k - 1];
             aux.segment_total[seg][2 * xq] = q[15].v[0];
@@ -1023,20 +1088,22 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 5 : 3) decom
             __syncthreads();
             const int xq = tid & 7, o = tid >> 3;  // o = z in the y pass, y in the z pass
             {
+                const strip_addr_y3<Bits> col(o, xq);
                 S q[16];
 #pragma unroll
-                for (int y = 0; y < 16; ++y) q[y] = S::load(tile, o * 256 + y * 16 + xq * 2);
+                for (int y = 0; y < 16; ++y) q[y] = S::load(tile + col.at(y));
 #pragma unroll
                 for (int y = 1; y < 16; ++y) {
                     q[y] = q[y] + q[y - 1];
-                    q[y].store(tile, o * 256 + y * 16 + xq * 2);
+                    q[y].store(tile + col.at(y));
                 }
             }
             __syncthreads();
             {
+                const strip_addr_z3<Bits> col(o, xq);
                 S q[16];
 #pragma unroll
-                for (int z = 0; z < 16; ++z) q[z] = S::load(tile, z * 256 + o * 16 + xq * 2);
+                for (int z = 0; z < 16; ++z) q[z] = S::load(tile + col.at(z));
                 const uint64_t plane = static_cast<uint64_t>(a.geom.n[1]) * a.geom.n[2];
                 Bits *dst = data + origin + static_cast<uint64_t>(o) * a.geom.n[2] + xq * 2;
                 q[0].template emit<Vec16>(dst);
@@ -1132,11 +1199,15 @@ using compress_ws_fn = void (*)(const compress_launch, const CUtensorMap);
 // (NDZB_WS_VARIANT) and are documented with their measurements in profiles/README.md
 struct ws_variant {
     int groups, retire, look_back_depth, ticket_lookahead, prefetch_limit;
+    int early;  // look-back started when the cube's length is known (1) / when its image is complete (0) / 1 for 3-D profiles only (2)
     bool stats;
 };
-constexpr ws_variant kWsVariants32[] = {{5, 3, 2, 1, 0, false}, {5, 4, 2, 1, 0, false}, {5, 5, 2, 1, 0, false}, {5, 6, 2, 1, 0, false},
-        {4, 4, 2, 1, 0, false}, {4, 5, 2, 1, 0, false}, {4, 6, 2, 1, 0, false}, {5, 5, 2, 1, 0, true}};
-constexpr ws_variant kWsVariants64[] = {{3, 2, 2, 1, 0, false}, {3, 3, 2, 1, 0, false}, {3, 4, 2, 1, 0, false}, {2, 3, 2, 1, 0, false}, {3, 3, 2, 1, 0, true}};
+// Variant 0 is what the library uses. Measured on B200 (profiles/README.md): 5 groups + 3 retire warps is the best
+// split for float, 3 + 2 for double; the early look-back gains 4.5 % on 3-D grids and loses 1-4 % on 1-D ones.
+constexpr ws_variant kWsVariants32[] = {{5, 3, 2, 1, 0, 2, false}, {5, 3, 2, 1, 0, 0, false}, {5, 3, 2, 1, 0, 1, false}, {4, 4, 2, 1, 0, 1, false},
+        {5, 3, 2, 1, 0, 2, true}};
+constexpr ws_variant kWsVariants64[] = {{3, 2, 2, 1, 0, 2, false}, {3, 2, 2, 1, 0, 0, false}, {3, 2, 2, 1, 0, 1, false}, {3, 3, 2, 1, 0, 1, false},
+        {3, 2, 2, 1, 0, 2, true}};
 constexpr int kNumWsVariants32 = sizeof(kWsVariants32) / sizeof(ws_variant);
 constexpr int kNumWsVariants64 = sizeof(kWsVariants64) / sizeof(ws_variant);
 
@@ -1144,34 +1215,23 @@ template<typename Bits, int Dims, int V>
 compress_ws_fn compress_ws_variant_fn() {
     if constexpr (sizeof(Bits) == 4) {
         constexpr ws_variant v = kWsVariants32[V];
-        return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.prefetch_limit, v.stats>;
+        return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.prefetch_limit,
+                v.early == 1 || (v.early == 2 && Dims == 3), v.stats>;
     } else {
         constexpr ws_variant v = kWsVariants64[V];
-        return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.prefetch_limit, v.stats>;
+        return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.prefetch_limit,
+                v.early == 1 || (v.early == 2 && Dims == 3), v.stats>;
     }
 }
 
 template<typename Bits, int Dims>
 compress_ws_fn compress_ws_for(int variant) {
-    if constexpr (sizeof(Bits) == 4) {
-        switch (variant) {
-            case 1: return compress_ws_variant_fn<Bits, Dims, 1>();
-            case 2: return compress_ws_variant_fn<Bits, Dims, 2>();
-            case 3: return compress_ws_variant_fn<Bits, Dims, 3>();
-            case 4: return compress_ws_variant_fn<Bits, Dims, 4>();
-            case 5: return compress_ws_variant_fn<Bits, Dims, 5>();
-            case 6: return compress_ws_variant_fn<Bits, Dims, 6>();
-            case 7: return compress_ws_variant_fn<Bits, Dims, 7>();
-            default: return compress_ws_variant_fn<Bits, Dims, 0>();
-        }
-    } else {
-        switch (variant) {
-            case 1: return compress_ws_variant_fn<Bits, Dims, 1>();
-            case 2: return compress_ws_variant_fn<Bits, Dims, 2>();
-            case 3: return compress_ws_variant_fn<Bits, Dims, 3>();
-            case 4: return compress_ws_variant_fn<Bits, Dims, 4>();
-            default: return compress_ws_variant_fn<Bits, Dims, 0>();
-        }
+    switch (variant) {
+        case 1: return compress_ws_variant_fn<Bits, Dims, 1>();
+        case 2: return compress_ws_variant_fn<Bits, Dims, 2>();
+        case 3: return compress_ws_variant_fn<Bits, Dims, 3>();
+        case 4: return compress_ws_variant_fn<Bits, Dims, 4>();
+        default: return compress_ws_variant_fn<Bits, Dims, 0>();
     }
 }
 compress_ws_fn compress_ws_entry(int dtype, int dims, int variant) {

@@ -160,7 +160,32 @@ grid_geom make_geom(int dims, const uint32_t *size) {
 
 }  // namespace
 
+template<typename Bits>
+int strip_address_mismatches() {
+    int bad = 0;
+    for (int o = 0; o < 16; ++o) {
+        for (int xq = 0; xq < 8; ++xq) {
+            const strip_addr_y3<Bits> ay(o, xq);
+            const strip_addr_z3<Bits> az(o, xq);
+            for (int k = 0; k < 16; ++k) {
+                bad += ay.at(k) != tile_elem<Bits>(o * 256 + k * 16 + xq * 2);
+                bad += az.at(k) != tile_elem<Bits>(k * 256 + o * 16 + xq * 2);
+            }
+        }
+    }
+    for (int seg = 0; seg < 4; ++seg) {
+        for (int xq = 0; xq < 32; ++xq) {
+            const strip_addr_y2<Bits> a(seg, xq);
+            for (int k = 0; k < 16; ++k) bad += a.at(k) != tile_elem<Bits>((seg * 16 + k) * 64 + xq * 2);
+        }
+    }
+    return bad;
+}
+
 extern "C" {
+
+// number of strip addresses (decoder column passes) that differ from tile_elem(); must be 0
+int sim_strip_address_mismatches() { return strip_address_mismatches<uint32_t>() + strip_address_mismatches<uint64_t>(); }
 
 // cube: 4096 raw words in cube-local order; out: compressed cube. Returns words written.
 uint32_t sim_encode_cube(int dtype, int dims, const void *cube, void *out) {

@@ -92,3 +92,9 @@ def test_cube_addressing_matches_oracle(sim, oracle, shape):
         cube = oracle.load_cube(data, hc)
         for e in (0, 1, 15, 16, 63, 64, 255, 256, 1000, 4095):
             assert sim.sim_cube_element_index(dims, size, hc, e) == int(cube[e])
+
+
+def test_decoder_strip_addresses_match_the_tile_layout(sim):
+    # strength-reduced addresses of the y / z column passes (strip_addr_*) == tile_elem() for every strip
+    sim.sim_strip_address_mismatches.restype = ctypes.c_int
+    assert sim.sim_strip_address_mismatches() == 0
