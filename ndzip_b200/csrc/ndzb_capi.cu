@@ -104,6 +104,7 @@ struct ndzb_ctx {
     bool ws_check = false;            // NDZB_WS_CHECK=1: synchronise after every launch and report a raised watchdog as an error
     unsigned long long *d_stats = nullptr;  // NDZB_WS_STATS=1: role/wait cycle counters of the Stats kernel variants, printed per launch
     uint32_t ws_debug = 0;            // NDZB_WS_DEBUG: profiling aids of compress_ws_kernel (produce invalid streams)
+    int dec_ctas_cap = 0;             // NDZB_DEC_CTAS=n: at most n resident decompress CTAs per SM (tuning runs)
     bool use_ws = true;               // NDZB_COMPRESS_KERNEL=v1 selects compress_kernel also for TMA-compatible inputs
     int ws_variant = 0;               // NDZB_WS_VARIANT=n: (encoder groups, retire warps) tuning variants
     uint32_t last_launches = 0;
@@ -247,7 +248,8 @@ bool store_vectorisable(const ndzb_ctx *ctx, const void *data, const grid_geom &
 int enqueue_decompress_range(ndzb_ctx *ctx, const void *stream_cubes, const uint32_t *offsets, void *d_data,
         const grid_geom &g, uint32_t hc_begin, uint32_t count) {
     const bool vec = store_vectorisable(ctx, d_data, g);
-    const int per_sm = g_config.dec_ctas_per_sm[ctx->dtype][ctx->dims - 1][vec ? 1 : 0];
+    int per_sm = g_config.dec_ctas_per_sm[ctx->dtype][ctx->dims - 1][vec ? 1 : 0];
+    if (ctx->dec_ctas_cap > 0 && per_sm > ctx->dec_ctas_cap) per_sm = ctx->dec_ctas_cap;  // NDZB_DEC_CTAS (tuning)
     const uint64_t resident = static_cast<uint64_t>(per_sm > 0 ? per_sm : 1) * g_config.num_sms;
     const uint32_t grid = static_cast<uint32_t>(count < resident ? count : resident);
     decompress_launch a{};
@@ -469,6 +471,7 @@ int ndzb_ctx_create(ndzb_ctx **out_ctx, int dtype, int dims, uint32_t max_hyperc
     }
     if (const char *p = getenv("NDZB_COMPRESS_KERNEL")) ctx->use_ws = strcmp(p, "v1") != 0;
     if (const char *p = getenv("NDZB_WS_VARIANT")) ctx->ws_variant = atoi(p);
+    if (const char *p = getenv("NDZB_DEC_CTAS")) ctx->dec_ctas_cap = atoi(p);
     auto fail = [&](int rc) {
         ndzb_ctx_destroy(ctx);
         return rc;

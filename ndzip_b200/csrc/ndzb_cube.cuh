@@ -504,31 +504,60 @@ template<> NDZB_HD void tile_store<uint64_t>(uint32_t *tile, int e, uint64_t v) 
 // base registers and everything else into the load/store immediate:  address(k) = base[sel(k)] + imm(k).
 // tests/host_sim checks every address against tile_elem().
 
+// Value tile of the 3-D float decoder: tile_unit() with the z parity XORed into bit 2 of the unit. In the
+// y pass a warp holds 4 z planes x 8 strips; plain tile_unit() puts the four planes on the same 16 banks
+// (2 x the minimum number of wavefronts, profiles/r1_r2a_decompress.txt: 42 % of all shared-memory
+// wavefronts were conflicts), with the parity term even and odd planes use complementary bank halves.
+// (The double tile already spreads 8 strips of 16 bytes over all banks.)
+NDZB_HD int tile3_unit(int row, int unit) { return (row << 5) | ((unit ^ (row & 7) ^ ((row >> 1) & 4)) << 2); }
+
+template<typename Bits> NDZB_HD int tile3_elem(int e);
+template<> NDZB_HD int tile3_elem<uint32_t>(int e) {
+    const int run = e >> 5, j = e & 31;
+    return tile3_unit(run, j >> 2) + (j & 3);
+}
+template<> NDZB_HD int tile3_elem<uint64_t>(int e) { return tile_elem<uint64_t>(e); }
+
+// store_run for the 3-D decoder's value tile
+NDZB_HD void store_run3(uint32_t *tile, int u, const uint32_t *r) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        st_quad(tile + tile3_unit(u, g), quad{r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]});
+    }
+}
+NDZB_HD void store_run3(uint32_t *tile, int u, const uint64_t *r) { store_run(tile, u, r); }
+
 // 3-D, y pass: strip (z = o, y = k, x = 2 xq)
 template<typename Bits>
 struct strip_addr_y3 {
-    static constexpr int kBases = sizeof(Bits) == 4 ? 4 : 8;
-    int base[kBases];
+    int base[8];
     NDZB_HD strip_addr_y3(int o, int xq) {
 #pragma unroll
-        for (int m = 0; m < kBases; ++m) {
-            if constexpr (sizeof(Bits) == 4) base[m] = o * 256 + (((xq >> 1) ^ m) << 2) + ((xq & 1) << 1);
-            else base[m] = o * 256 + ((xq ^ m) << 2);
+        for (int m = 0; m < 8; ++m) {
+            if constexpr (sizeof(Bits) == 4) {
+                // m = (unit bit 2 known at compile time) * 4 + (XOR constant of unit bits 0-1)
+                base[m] = o * 256 + (((xq >> 1) ^ (m & 3)) << 2) + ((((m >> 2) ^ o) & 1) << 4) + ((xq & 1) << 1);
+            } else {
+                base[m] = o * 256 + ((xq ^ m) << 2);
+            }
         }
     }
     NDZB_HD int at(int k) const {
         const int c = k >> 1;
-        if constexpr (sizeof(Bits) == 4) return base[c & 3] + c * 32 + ((((k & 1) * 4) ^ (c & 4)) << 2);
+        if constexpr (sizeof(Bits) == 4) return base[(((k & 1) ^ (c >> 2)) << 2) | (c & 3)] + c * 32;
         else return base[c] + (k & 1) * 4096 + c * 32;
     }
 };
 
-// 3-D, z pass: strip (z = k, y = o, x = 2 xq) — the swizzle does not depend on z
+// 3-D, z pass: strip (z = k, y = o, x = 2 xq) — the swizzle only depends on the parity of z
 template<typename Bits>
 struct strip_addr_z3 {
-    int base;
-    NDZB_HD strip_addr_z3(int o, int xq) : base(tile_elem<Bits>(o * 16 + xq * 2)) {}
-    NDZB_HD int at(int k) const { return base + k * 256; }
+    int base[2];
+    NDZB_HD strip_addr_z3(int o, int xq) {
+        base[0] = tile3_elem<Bits>(o * 16 + xq * 2);
+        base[1] = tile3_elem<Bits>(256 + o * 16 + xq * 2) - 256;
+    }
+    NDZB_HD int at(int k) const { return base[k & 1] + k * 256; }
 };
 
 // 2-D, y pass: strip (y = 16 seg + k, x = 2 xq), xq < 32

@@ -921,7 +921,7 @@ __device__ __forceinline__ void stream_in_cube(uint32_t *buf, const Bits *stream
 }
 
 template<typename Bits, int Dims, bool Vec16>
-__global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 5 : 3) decompress_kernel(const decompress_launch a) {
+__global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decompress_kernel(const decompress_launch a) {
     using tr = codec_traits<Bits>;
     constexpr int buf_words = decode_plan<Bits>::buffer_bytes / 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1084,7 +1084,7 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 5 : 3) decom
             }
         } else {
             // ---- y direction in the tile, z direction fused with rotate + store; 16 x 8 strips per pass -
-            store_run(tile, tid, r);
+            store_run3(tile, tid, r);
             __syncthreads();
             const int xq = tid & 7, o = tid >> 3;  // o = z in the y pass, y in the z pass
             {

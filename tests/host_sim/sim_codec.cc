@@ -168,8 +168,8 @@ int strip_address_mismatches() {
             const strip_addr_y3<Bits> ay(o, xq);
             const strip_addr_z3<Bits> az(o, xq);
             for (int k = 0; k < 16; ++k) {
-                bad += ay.at(k) != tile_elem<Bits>(o * 256 + k * 16 + xq * 2);
-                bad += az.at(k) != tile_elem<Bits>(k * 256 + o * 16 + xq * 2);
+                bad += ay.at(k) != tile3_elem<Bits>(o * 256 + k * 16 + xq * 2);
+                bad += az.at(k) != tile3_elem<Bits>(k * 256 + o * 16 + xq * 2);
             }
         }
     }
