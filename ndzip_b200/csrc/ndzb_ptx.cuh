@@ -78,6 +78,13 @@ __device__ __forceinline__ void tma_load_4d(
             : "memory");
 }
 
+// ---- bulk copy global -> shared (no tensor map): 16-byte aligned source, destination and size -----
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+            "l"(src), "r"(bytes), "r"(smem_addr(bar))
+            : "memory");
+}
+
 // ---- TMA tensor store: shared -> global (bulk async-group completion) ---------------------------
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
