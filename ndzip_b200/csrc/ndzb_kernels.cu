@@ -109,13 +109,13 @@ using look_back_sample = look_back_window<kLookBackDepth>;
 
 // Loads the descriptors of the window ending at predecessor `idx` (lane l: idx-l, idx-32-l, ...).
 // Positions before cube 0 read as a published prefix equal to the launch's base offset.
-template<int Depth = kLookBackDepth>
+template<int Depth = kLookBackDepth, bool Cg = false>
 __device__ __forceinline__ look_back_window<Depth> look_back_load(const uint64_t *desc, int64_t idx, uint32_t epoch, int lane, uint32_t base) {
     look_back_window<Depth> s;
 #pragma unroll
     for (int k = 0; k < Depth; ++k) {
         const int64_t mine = idx - 32 * k - lane;
-        s.d[k] = mine >= 0 ? ptx::ld_relaxed_gpu(desc + mine) : pack_desc(epoch, kStatusPrefix, base);
+        s.d[k] = mine >= 0 ? (Cg ? ptx::ld_cg(desc + mine) : ptx::ld_relaxed_gpu(desc + mine)) : pack_desc(epoch, kStatusPrefix, base);
     }
     return s;
 }
@@ -165,7 +165,7 @@ struct watchdog {
 
 // `first` is a sample of the first window taken earlier (its L2 latency hidden behind other work).
 // Returns the exclusive offset; `*aborted` (optional) is set when the watchdog gave up.
-template<int Depth = kLookBackDepth>
+template<int Depth = kLookBackDepth, bool Cg = false>
 __device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, uint32_t epoch, int lane, look_back_window<Depth> first,
         uint32_t base, uint32_t *watch = nullptr, bool *aborted = nullptr, uint32_t *polls = nullptr) {
     uint32_t exclusive = 0;
@@ -196,7 +196,7 @@ __device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, 
             }
             __nanosleep(20);
             if (polls) *polls += 1u;
-            s = look_back_load<Depth>(desc, idx, epoch, lane, base);
+            s = look_back_load<Depth, Cg>(desc, idx, epoch, lane, base);
         }
 #pragma unroll
         for (int k = 0; k < Depth; ++k) {
@@ -207,7 +207,7 @@ __device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, 
         }
         idx -= 32 * Depth;
         if (polls) *polls += 0x10000u;
-        s = look_back_load<Depth>(desc, idx, epoch, lane, base);
+        s = look_back_load<Depth, Cg>(desc, idx, epoch, lane, base);
     }
 }
 
@@ -796,9 +796,14 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             if (a.debug_flags & 2u) {
                 exclusive = t * static_cast<uint32_t>(tr::max_cube_words);  // profiling aid: no look-back, fixed-stride output (NOT the stream format)
             } else if (t != 0) {
-                const look_back_window<LB> first = look_back_load<LB>(a.desc, static_cast<int64_t>(t) - 1, a.epoch, lane, launch_base);
                 bool aborted = false;
-                exclusive = look_back<LB>(a.desc, t, a.epoch, lane, first, launch_base, a.watch, &aborted, Stats ? &st_polls : nullptr);
+                if constexpr (LB < 0) {  // windows of 32 * -LB cubes read with weak L1-bypassing loads (ld.global.cg)
+                    const look_back_window<-LB> first = look_back_load<-LB, true>(a.desc, static_cast<int64_t>(t) - 1, a.epoch, lane, launch_base);
+                    exclusive = look_back<-LB, true>(a.desc, t, a.epoch, lane, first, launch_base, a.watch, &aborted, Stats ? &st_polls : nullptr);
+                } else {
+                    const look_back_window<LB> first = look_back_load<LB>(a.desc, static_cast<int64_t>(t) - 1, a.epoch, lane, launch_base);
+                    exclusive = look_back<LB>(a.desc, t, a.epoch, lane, first, launch_base, a.watch, &aborted, Stats ? &st_polls : nullptr);
+                }
                 if (aborted) break;
             }
             const long long c2 = now();
@@ -1237,7 +1242,7 @@ struct ws_variant {
 };
 // Variant 0 is what the library uses. Measured on B200 (profiles/README.md): 5 groups + 3 retire warps is the best
 // split for float, 3 + 2 for double; the early look-back gains 4.5 % on 3-D grids and loses 1-4 % on 1-D ones.
-constexpr ws_variant kWsVariants32[] = {{5, 3, 2, 1, 0, 2, false}, {5, 3, 2, 1, 0, 0, false}, {5, 3, 2, 1, 0, 1, false}, {4, 4, 2, 1, 0, 1, false},
+constexpr ws_variant kWsVariants32[] = {{5, 3, 2, 1, 0, 2, false}, {5, 3, 2, 1, 0, 0, false}, {5, 3, -2, 1, 0, 1, false}, {4, 4, 2, 1, 0, 1, false},
         {5, 3, 2, 1, 0, 2, true}};
 constexpr ws_variant kWsVariants64[] = {{3, 2, 2, 1, 0, 2, false}, {3, 2, 2, 1, 0, 0, false}, {3, 2, 2, 1, 0, 1, false}, {3, 3, 2, 1, 0, 1, false},
         {3, 2, 2, 1, 0, 2, true}};

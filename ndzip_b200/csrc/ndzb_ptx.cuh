@@ -128,6 +128,13 @@ __device__ __forceinline__ uint64_t ld_relaxed_gpu(const uint64_t *p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// The same word read with a weak L1-bypassing load. (Several ld.relaxed.gpu in a row appear to be executed one
+// round trip after the other; see profiles/README.md, look-back depth experiments.)
+__device__ __forceinline__ uint64_t ld_cg(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_relaxed_gpu(uint64_t *p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
