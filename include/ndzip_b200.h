@@ -73,6 +73,12 @@ int ndzb_offload_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uin
 int ndzb_offload_decompress(ndzb_ctx *ctx, const void *h_stream, uint32_t length_words, void *h_data, int dims,
         const uint32_t *size, uint32_t *consumed_words, uint64_t *kernel_ns);
 
+/* Page-locked host memory for the buffers handed to the two calls above (the offloader overlaps H2D, kernels
+ * and D2H only from pinned memory; pageable buffers work, more slowly). Used by tools/ndzip_compress.cc in place of
+ * the reference tool's malloc'ed / mmap'ed chunks (reference src/io/io.cc:23-24, 75-76). */
+int ndzb_host_alloc(void **out_ptr, size_t bytes);
+void ndzb_host_free(void *ptr);
+
 /* Multi-GPU sharding (new work; nothing to replace in the reference).
  * A rank compresses the hypercube range [hc_begin, hc_end) of the global array `size` that is fully
  * resident on its device (`d_data` points at the global array's element 0 as seen by this rank, i.e.

@@ -35,6 +35,24 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+TOOL_SRC = os.path.join(os.path.dirname(HERE), "tools", "ndzip_compress.cc")
+TOOL = os.path.join(HERE, "bin", "ndzip-compress")
+
+
+def build_tool(force: bool = False) -> str:
+    """Compile the command-line front end (tools/ndzip_compress.cc) against the C ABI. Returns the binary's path."""
+    deps = [TOOL_SRC, LIB, os.path.join(os.path.dirname(HERE), "include", "ndzip_b200.h")]
+    if not force and os.path.exists(TOOL) and all(os.path.getmtime(d) <= os.path.getmtime(TOOL) for d in deps if os.path.exists(d)):
+        return TOOL
+    os.makedirs(os.path.dirname(TOOL), exist_ok=True)
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", TOOL, TOOL_SRC, "-L" + HERE, "-lndzip_b200",
+                    "-Wl,-rpath,$ORIGIN/.."], check=True, env=env)
+    return TOOL
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library if missing or older than its sources. Returns the .so path."""
     if not force and not _stale():
@@ -53,3 +71,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_tool(force=True))

@@ -508,6 +508,17 @@ int ndzb_ctx_create(ndzb_ctx **out_ctx, int dtype, int dims, uint32_t max_hyperc
     return NDZB_OK;
 }
 
+int ndzb_host_alloc(void **out_ptr, size_t bytes) {
+    if (!out_ptr) return NDZB_ERR_INVALID_ARGUMENT;
+    *out_ptr = nullptr;
+    NDZB_CUDA(cudaHostAlloc(out_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return NDZB_OK;
+}
+
+void ndzb_host_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
 void ndzb_ctx_destroy(ndzb_ctx *ctx) {
     if (!ctx) return;
     if (ctx->d_desc) cudaFree(ctx->d_desc);
