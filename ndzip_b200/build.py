@@ -35,21 +35,27 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-TOOL_SRC = os.path.join(os.path.dirname(HERE), "tools", "ndzip_compress.cc")
-TOOL = os.path.join(HERE, "bin", "ndzip-compress")
+TOOLS_DIR = os.path.join(os.path.dirname(HERE), "tools")
+BIN_DIR = os.path.join(HERE, "bin")
+TOOLS = {"ndzip-compress": "ndzip_compress.cc", "ndzip-benchmark": "ndzip_benchmark.cc"}
+TOOL = os.path.join(BIN_DIR, "ndzip-compress")
+BENCHMARK_TOOL = os.path.join(BIN_DIR, "ndzip-benchmark")
 
 
 def build_tool(force: bool = False) -> str:
-    """Compile the command-line front end (tools/ndzip_compress.cc) against the C ABI. Returns the binary's path."""
-    deps = [TOOL_SRC, LIB, os.path.join(os.path.dirname(HERE), "include", "ndzip_b200.h")]
-    if not force and os.path.exists(TOOL) and all(os.path.getmtime(d) <= os.path.getmtime(TOOL) for d in deps if os.path.exists(d)):
-        return TOOL
-    os.makedirs(os.path.dirname(TOOL), exist_ok=True)
+    """Compile the command-line tools (tools/*.cc, counterparts of the reference's `compress` and `benchmark`)
+    against the C ABI with plain g++. Returns the path of ndzip-compress."""
+    os.makedirs(BIN_DIR, exist_ok=True)
     env = dict(os.environ)
     env.pop("CXX", None)
     env.pop("CC", None)
-    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", TOOL, TOOL_SRC, "-L" + HERE, "-lndzip_b200",
-                    "-Wl,-rpath,$ORIGIN/.."], check=True, env=env)
+    for name, src in TOOLS.items():
+        out, src = os.path.join(BIN_DIR, name), os.path.join(TOOLS_DIR, src)
+        deps = [src, LIB, os.path.join(os.path.dirname(HERE), "include", "ndzip_b200.h")]
+        if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps if os.path.exists(d)):
+            continue
+        subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", out, src, "-L" + HERE, "-lndzip_b200",
+                        "-Wl,-rpath,$ORIGIN/.."], check=True, env=env)
     return TOOL
 
 

@@ -86,3 +86,54 @@ def test_pipes_and_partial_chunks(tool, oracle):
     assert r2.returncode == 0 and r2.stdout == data.tobytes()
     r3 = run(tool, "-n", str(shape[0]), stdin=data.tobytes()[:-4])  # reference io.cc:62
     assert r3.returncode == 1 and b"not a multiple of the chunk size" in r3.stderr
+
+
+# ---- tools/ndzip_benchmark.cc: the ndzip-cuda column of the reference's benchmark driver -------------------------
+BENCH_HEADER = ("dataset;data type;dimensions;algorithm;tunable;number of threads;compression times (microseconds);"
+                "decompression times (microseconds);uncompressed bytes;compressed bytes")  # reference benchmark.cc:1487-1489
+
+
+@pytest.fixture(scope="module")
+def bench_tool(tool):
+    from ndzip_b200 import build
+    return build.BENCHMARK_TOOL
+
+
+def test_benchmark_driver_usage(bench_tool, tmp_path):
+    assert run(bench_tool, "--help").returncode == 0
+    r = run(bench_tool)
+    assert r.returncode == 1 and b"csv-file" in r.stderr
+    r = run(bench_tool, str(tmp_path / "missing.csv"))
+    assert r.returncode == 1
+    r = run(bench_tool, "-a", "zfp", str(tmp_path / "x.csv"))
+    assert r.returncode == 1 and b"ndzip-cuda" in r.stderr
+    bad = tmp_path / "bad.csv"
+    bad.write_text("a.f32;half;16\n")
+    r = run(bench_tool, str(bad))
+    assert r.returncode == 1 and b"invalid data type" in r.stderr
+
+
+@pytest.mark.gpu
+def test_benchmark_driver_rows_match_the_reference_schema(bench_tool, oracle, tmp_path):
+    import io
+    import pandas as pd
+    sets = [("smooth.f32", "float32", (48, 64, 80)), ("grid.f64", "float64", (130, 200)), ("line.f32", "float32", (5 * 4096 + 3,))]
+    lines = []
+    for name, dtype, shape in sets:
+        synth.smooth(shape, dtype, seed=31).tofile(tmp_path / name)
+        lines.append(f"{name};{'float' if dtype == 'float32' else 'double'};{' '.join(map(str, shape))}")
+    (tmp_path / "sets.csv").write_text("\n".join(lines) + "\n")
+    r = run(bench_tool, str(tmp_path / "sets.csv"), "-r", "3", "-t", "1", "-a", "ndzip-cuda")
+    assert r.returncode == 0, r.stderr.decode()
+    out = r.stdout.decode()
+    assert out.splitlines()[0] == BENCH_HEADER
+    df = pd.read_csv(io.StringIO(out), sep=";")  # what the reference's plot_benchmark.py does
+    assert list(df["dataset"]) == [s[0] for s in sets]
+    assert set(df["algorithm"]) == {"ndzip-cuda"}
+    for (name, dtype, shape), (_, row) in zip(sets, df.iterrows()):
+        data = np.fromfile(tmp_path / name, dtype=dtype).reshape(shape)
+        assert row["dimensions"] == len(shape) and row["data type"] == ("float" if dtype == "float32" else "double")
+        assert row["uncompressed bytes"] == data.nbytes
+        assert row["compressed bytes"] == oracle.compress(data).nbytes
+        assert len(str(row["compression times (microseconds)"]).split(",")) >= 3
+        assert len(str(row["decompression times (microseconds)"]).split(",")) >= 3

@@ -157,6 +157,34 @@ def test_many_incompressible_cubes_and_misaligned_stream_pointer(nz, oracle, dty
     assert int(backing[0].item()) == 0
 
 
+def test_repeated_launches_on_one_dimensional_input_stay_identical(nz, monkeypatch):
+    # regression: 1-D inputs have the shortest cube period; a TMA load slower than one round of the slot ring
+    # let an encoder group pass its mbarrier parity wait one phase early (about one launch in 30 at this size),
+    # the cube's length was never published and the kernel spun. NDZB_WS_CHECK turns a raised watchdog into
+    # an error instead of a trap, so a recurrence fails this test instead of poisoning the CUDA context.
+    import torch
+    monkeypatch.setenv("NDZB_WS_CHECK", "1")
+    shape = (16384 * 4096,)
+    d_in = torch.from_numpy(synth.smooth((1 << 20,), "float32", seed=9)).cuda().repeat(64)
+    d_in += torch.arange(d_in.numel(), device="cuda", dtype=torch.float32) * 1e-7  # no two cubes alike
+    comp = nz.make_cuda_compressor("float32", nz.compressor_requirements(shape))
+    d_stream = torch.zeros(nz.compressed_length_bound("float32", shape), dtype=torch.int32, device="cuda")
+    d_len = torch.zeros(1, dtype=torch.int32, device="cuda")
+    first = None
+    for i in range(40):
+        comp.compress(d_in, shape, d_stream, d_len)
+        torch.cuda.synchronize()
+        n = int(d_len.item())
+        if i in (0, 1, 39):
+            digest = (n, zlib.crc32(d_stream[:n].cpu().numpy().tobytes()))
+            first = first or digest
+            assert digest == first
+    back = torch.zeros_like(d_in)
+    nz.make_cuda_decompressor("float32", 1).decompress(d_stream, back, shape)
+    torch.cuda.synchronize()
+    assert torch.equal(back.view(torch.int32), d_in.view(torch.int32))
+
+
 @pytest.mark.parametrize("dtype,dims", PROFILES)
 @pytest.mark.parametrize("n", [0, 1])
 def test_zero_hypercube_extents(nz, oracle, dtype, dims, n):
