@@ -507,6 +507,8 @@ struct ws_aux {
     uint32_t issued[S];  // Stats instantiations: clock (low word) at which the slot's TMA load was issued
     uint32_t freed[S];   //                       clock at which the slot was handed back to the loader
     uint32_t warp_total[2][G][4];
+    uint32_t next_seq;         // Dyn: the next of the CTA's cubes that no encoder group has taken yet
+    uint32_t group_seq[2][G];  // Dyn: the cube each group took (double-buffered)
 };
 
 template<typename Bits>
@@ -562,7 +564,7 @@ __device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *ds
     if (w < n) dst[w] = img[w];
 }
 
-template<typename Bits, int Dims, int G, int R, int LB, int LA, int PF, bool Early, bool Stats>
+template<typename Bits, int Dims, int G, int R, int LB, int LA, int PF, bool Early, bool Dyn, bool Stats>
 __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
         compress_ws_kernel(const compress_launch a, const __grid_constant__ CUtensorMap in_map) {
     using tr = codec_traits<Bits>;
@@ -586,6 +588,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             ptx::mbar_init(&aux.taken[s], 1);
             ptx::mbar_init(&aux.counted[s], 1);
         }
+        aux.next_seq = 0;
         ptx::fence_mbar_init();
     }
     __syncthreads();  // the only CTA-wide barrier; the roles below never meet again
@@ -597,9 +600,21 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
     if (warp < 4 * G) {
         // ---------------------------------------------------------------------------------- encoder
         const int g = warp >> 2, u = tid & (kCubeThreads - 1), wg = warp & 3;
+        // Static (cube g, g+G, ... per group) or dynamic assignment (Dyn: the group that becomes free takes the CTA's
+        // next cube). With static assignment a tile that lands while its group is still busy waits although other
+        // groups idle, and every cube behind it in the stream waits for its length.
+        static_assert(!Dyn || (G >= R && PF == 0), "dynamic assignment: one end marker per group, no prefetch limit");
         int s = g;
-        uint32_t parity = 0, flip = 0, seq = g;
+        uint32_t parity = 0, flip = 0, seq = g, grabs = 0;
         for (;; seq += G) {
+            if constexpr (Dyn) {
+                if (wg == 0 && lane == 0) aux.group_seq[grabs & 1u][g] = atomicAdd(&aux.next_seq, 1u);
+                ptx::named_barrier(1 + g, kCubeThreads);
+                seq = aux.group_seq[grabs & 1u][g];
+                ++grabs;
+                s = static_cast<int>(seq % static_cast<uint32_t>(S));
+                parity = (seq / static_cast<uint32_t>(S)) & 1u;
+            }
             // A parity wait cannot tell "phase r completed" from "phase r-1 still running": when the TMA load of
             // the cube one ring round back is slower than this group (seen on 1-D inputs, about once in 10^5
             // cubes), the wait falls through while the slot still belongs to that cube. The slot's sequence
@@ -624,7 +639,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                 // that is addressed to this group
                 if (Early && u == 0) ptx::mbar_arrive(&aux.counted[s]);
                 ptx::mbar_arrive(&aux.done[s]);
-                if ((kNoTicket - t) + G >= kPoison) break;
+                if (Dyn || (kNoTicket - t) + G >= kPoison) break;
                 s += G;
                 if (s >= S) {
                     s -= S;
@@ -1236,16 +1251,22 @@ using compress_ws_fn = void (*)(const compress_launch, const CUtensorMap);
 // (encoder groups, retire warps) per CTA; variant 0 is the default, the others exist for tuning runs
 // (NDZB_WS_VARIANT) and are documented with their measurements in profiles/README.md
 struct ws_variant {
-    int groups, retire, look_back_depth, ticket_lookahead, prefetch_limit;
+    int groups, retire;
+    int look_back_depth;  // windows of 32 * depth cubes per round trip (negative: read with ld.global.cg)
+    int ticket_lookahead, prefetch_limit;
     int early;  // look-back started when the cube's length is known (1) / when its image is complete (0) / 1 for 3-D profiles only (2)
+    bool dynamic;  // encoder groups take the CTA's next cube when they become free (instead of cube g, g+G, ...)
     bool stats;
 };
-// Variant 0 is what the library uses. Measured on B200 (profiles/README.md): 5 groups + 3 retire warps is the best
-// split for float, 3 + 2 for double; the early look-back gains 4.5 % on 3-D grids and loses 1-4 % on 1-D ones.
-constexpr ws_variant kWsVariants32[] = {{5, 3, 2, 1, 0, 2, false}, {5, 3, 2, 1, 0, 0, false}, {5, 3, -2, 1, 0, 1, false}, {4, 4, 2, 1, 0, 1, false},
-        {5, 3, 2, 1, 0, 2, true}};
-constexpr ws_variant kWsVariants64[] = {{3, 2, 2, 1, 0, 2, false}, {3, 2, 2, 1, 0, 0, false}, {3, 2, 2, 1, 0, 1, false}, {3, 3, 2, 1, 0, 1, false},
-        {3, 2, 2, 1, 0, 2, true}};
+// Variant 0 is what the library uses; 1-4 are kept for A/B runs and so that the tests cover every code path (late
+// look-back, dynamic assignment, weak descriptor loads, prefetch limit + statistics). Measured on B200
+// (profiles/README.md): 5 groups + 3 retire warps is the best split for float, 3 + 2 for double; the early look-back
+// gains 4.5 % on 3-D grids and loses 1-4 % on 1-D ones; dynamic assignment gains 3 % on 3-D float and loses 6-10 %
+// elsewhere.
+constexpr ws_variant kWsVariants32[] = {{5, 3, 2, 1, 0, 2, false, false}, {5, 3, 2, 1, 0, 0, false, false}, {5, 3, 2, 1, 0, 1, true, false},
+        {4, 4, -2, 1, 0, 1, false, false}, {5, 3, 2, 1, 3, 2, false, true}};
+constexpr ws_variant kWsVariants64[] = {{3, 2, 2, 1, 0, 2, false, false}, {3, 2, 2, 1, 0, 0, false, false}, {3, 2, 2, 1, 0, 1, true, false},
+        {3, 3, -2, 1, 0, 1, false, false}, {3, 2, 2, 1, 2, 2, false, true}};
 constexpr int kNumWsVariants32 = sizeof(kWsVariants32) / sizeof(ws_variant);
 constexpr int kNumWsVariants64 = sizeof(kWsVariants64) / sizeof(ws_variant);
 
@@ -1254,11 +1275,11 @@ compress_ws_fn compress_ws_variant_fn() {
     if constexpr (sizeof(Bits) == 4) {
         constexpr ws_variant v = kWsVariants32[V];
         return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.prefetch_limit,
-                v.early == 1 || (v.early == 2 && Dims == 3), v.stats>;
+                v.early == 1 || (v.early == 2 && Dims == 3), v.dynamic, v.stats>;
     } else {
         constexpr ws_variant v = kWsVariants64[V];
         return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.prefetch_limit,
-                v.early == 1 || (v.early == 2 && Dims == 3), v.stats>;
+                v.early == 1 || (v.early == 2 && Dims == 3), v.dynamic, v.stats>;
     }
 }
 
