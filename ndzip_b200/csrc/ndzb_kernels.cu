@@ -124,7 +124,7 @@ __device__ __forceinline__ look_back_window<Depth> look_back_load(const uint64_t
 // stuck for kWatchdogCycles raises the flag; every spin loop polls it. Every warp that abandons a wait
 // appends a record {code, block, thread, x, y, z} at watch[8 + 6 * i] (i < kWatchRecords), so the host sees
 // the whole wait-for graph. watch[7] == 0 (production): trap right away instead.
-constexpr long long kWatchdogCycles = 4000000000ll;  // ~2 s
+constexpr long long kWatchdogCycles = 20000000000ll;  // ~10 s at 1.9 GHz: far beyond any legitimate wait, also under a profiler
 constexpr uint32_t kWatchRecords = 4000;
 constexpr uint32_t kWatchWords = 8 + 6 * kWatchRecords;
 static_assert(kWatchWords <= kWatchdogWords, "watchdog buffer too small");
