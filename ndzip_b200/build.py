@@ -65,6 +65,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
     cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(os.path.dirname(HERE), "include"), "-o", LIB, *srcs]
+    if os.environ.get("NDZB_EXTRA_NVCC_FLAGS"):  # tuning builds, e.g. -DNDZB_DESC_STRIDE=4
+        cmd[1:1] = os.environ["NDZB_EXTRA_NVCC_FLAGS"].split()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     # nvcc must use the system g++ (the CXX in this image's environment points at a wrapper without libgomp specs)

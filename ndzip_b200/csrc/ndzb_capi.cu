@@ -96,6 +96,7 @@ struct ndzb_ctx {
     cudaStream_t stream = nullptr;
     uint32_t desc_capacity = 0;
     uint64_t *d_desc = nullptr;       // look-back descriptors
+    unsigned long long *d_blocks = nullptr;  // block-level look-back words (one per 32 cubes), same capacity as d_desc
     uint32_t *d_counters = nullptr;   // [0] ticket counter, [1] total compressed words of the last launch
     uint32_t ticket_base = 0;
     uint32_t epoch = 1;
@@ -128,10 +129,13 @@ int ensure_descriptors(ndzb_ctx *ctx, uint32_t cubes) {
     // Growing synchronises the device (cudaFree/cudaMalloc); contexts sized by
     // compressor_requirements never get here.
     if (ctx->d_desc) NDZB_CUDA(cudaFree(ctx->d_desc));
+    if (ctx->d_blocks) NDZB_CUDA(cudaFree(ctx->d_blocks));
+    ctx->d_blocks = nullptr;
+    NDZB_CUDA(cudaMalloc(&ctx->d_blocks, (static_cast<size_t>(cubes) / 32 + 1) * kDescStride * sizeof(unsigned long long)));
     ctx->d_desc = nullptr;
     ctx->desc_capacity = 0;
-    NDZB_CUDA(cudaMalloc(&ctx->d_desc, static_cast<size_t>(cubes) * sizeof(uint64_t)));
-    NDZB_CUDA(cudaMemsetAsync(ctx->d_desc, 0, static_cast<size_t>(cubes) * sizeof(uint64_t), ctx->stream));
+    NDZB_CUDA(cudaMalloc(&ctx->d_desc, static_cast<size_t>(cubes) * kDescStride * sizeof(uint64_t)));
+    NDZB_CUDA(cudaMemsetAsync(ctx->d_desc, 0, static_cast<size_t>(cubes) * kDescStride * sizeof(uint64_t), ctx->stream));
     ctx->desc_capacity = cubes;
     return NDZB_OK;
 }
@@ -190,6 +194,10 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
     a.debug_flags = ctx->ws_debug;
     a.stats = ctx->d_stats;
     if (ws) {
+        a.block_desc = ctx->d_blocks;
+        if (compress_ws_uses_blocks(ctx->dtype, ctx->ws_variant)) {
+            NDZB_CUDA(cudaMemsetAsync(ctx->d_blocks, 0, (static_cast<size_t>(count) / 32 + 1) * kDescStride * sizeof(unsigned long long), ctx->stream));
+        }
         const cudaError_t e = launch_compress_ws(ctx->dtype, ctx->dims, ctx->ws_variant, a, map, grid, ctx->stream);
         if (e != cudaSuccess) return cuda_fail(e, "compress_ws_kernel launch");
         ctx->ticket_base += count + compress_ws_ticket_overdraw(ctx->dtype, ctx->ws_variant, grid);  // wraps together with the device counter
@@ -235,7 +243,7 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
     }
     ctx->last_launches += 1;
     if (++ctx->epoch >= (1u << 30)) {
-        NDZB_CUDA(cudaMemsetAsync(ctx->d_desc, 0, static_cast<size_t>(ctx->desc_capacity) * sizeof(uint64_t), ctx->stream));
+        NDZB_CUDA(cudaMemsetAsync(ctx->d_desc, 0, static_cast<size_t>(ctx->desc_capacity) * kDescStride * sizeof(uint64_t), ctx->stream));
         ctx->epoch = 1;
     }
     return NDZB_OK;
@@ -523,6 +531,7 @@ void ndzb_ctx_destroy(ndzb_ctx *ctx) {
     if (!ctx) return;
     if (ctx->d_desc) cudaFree(ctx->d_desc);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_blocks) cudaFree(ctx->d_blocks);
     if (ctx->d_watch) cudaFree(ctx->d_watch);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->d_in) cudaFree(ctx->d_in);

@@ -115,7 +115,7 @@ __device__ __forceinline__ look_back_window<Depth> look_back_load(const uint64_t
 #pragma unroll
     for (int k = 0; k < Depth; ++k) {
         const int64_t mine = idx - 32 * k - lane;
-        s.d[k] = mine >= 0 ? (Cg ? ptx::ld_cg(desc + mine) : ptx::ld_relaxed_gpu(desc + mine)) : pack_desc(epoch, kStatusPrefix, base);
+        s.d[k] = mine >= 0 ? (Cg ? ptx::ld_cg(desc + mine * kDescStride) : ptx::ld_relaxed_gpu(desc + mine * kDescStride)) : pack_desc(epoch, kStatusPrefix, base);
     }
     return s;
 }
@@ -208,6 +208,83 @@ __device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, 
         idx -= 32 * Depth;
         if (polls) *polls += 0x10000u;
         s = look_back_load<Depth, Cg>(desc, idx, epoch, lane, base);
+    }
+}
+
+// ---- two-level look-back ---------------------------------------------------------------------------
+// look_back() above walks back 32 * Depth cubes per L2 round trip; at ~170 cubes/us the nearest published offset is
+// 2-4 windows away, and every window is a dependent round trip of ~1000 cycles. Here cubes are grouped into blocks
+// of 32 consecutive tickets with one 64-bit word per block,
+//   [63:40] number of its cubes whose length is known, [39:0] sum of those lengths,
+// accumulated with one fire-and-forget atomic per cube (zeroed by the host before the launch). A look-back reads
+// the cubes before it in its own block (one per lane) and, per lane, one earlier block: its sum and the inclusive
+// offset published by the block's last cube. One round trip covers 1024 cubes.
+constexpr uint32_t kBlockShift = 5, kBlockCubes = 1u << kBlockShift;
+__device__ __forceinline__ uint64_t block_contribution(uint32_t words) { return (1ull << 40) | words; }
+
+__device__ __forceinline__ uint32_t look_back_blocks(const uint64_t *desc, const uint64_t *blocks, uint32_t t, uint32_t epoch, int lane,
+        uint32_t base, uint32_t *watch, bool *aborted, uint32_t *polls) {
+    const uint32_t first_of_block = t & ~(kBlockCubes - 1u);
+    const bool own_present = static_cast<uint32_t>(lane) < t - first_of_block;  // lane l: cube t-1-l, if in t's block
+    const uint64_t *own_ptr = desc + static_cast<size_t>(t - 1u - static_cast<uint32_t>(lane)) * kDescStride;
+    uint64_t own = own_present ? ptx::ld_relaxed_gpu(own_ptr) : 0ull;
+    // lane l: block (t / 32) - 1 - l; "block -1" is the launch's base offset, published from the start
+    int64_t m = static_cast<int64_t>(t >> kBlockShift) - 1 - lane;
+    auto block_word = [&](int64_t b) { return blocks + b * kDescStride; };
+    auto block_end = [&](int64_t b) { return desc + ((b << kBlockShift) + (kBlockCubes - 1)) * kDescStride; };
+    uint64_t blk = m >= 0 ? ptx::ld_relaxed_gpu(block_word(m)) : 0ull;
+    uint64_t pfx = m >= 0 ? ptx::ld_relaxed_gpu(block_end(m)) : pack_desc(epoch, kStatusPrefix, base);
+    watchdog dog(watch);
+
+    // ---- own block: the cubes between the block's start (or a published offset inside it) and t
+    uint32_t sum;
+    while (true) {
+        const uint32_t st = own_present ? desc_status(own, epoch) : kStatusAggregate;
+        const uint32_t prefix = __ballot_sync(kFullMask, own_present && st == kStatusPrefix);
+        const uint32_t invalid = __ballot_sync(kFullMask, st == 0);
+        const int nearest = prefix ? __ffs(prefix) - 1 : 32;
+        const uint32_t need = invalid & (prefix ? (1u << nearest) - 1u : 0xffffffffu);
+        if (need == 0) {
+            sum = __reduce_add_sync(kFullMask, own_present && lane <= nearest ? static_cast<uint32_t>(own) : 0u);
+            if (prefix) return sum;
+            break;
+        }
+        if (__any_sync(kFullMask, dog.expired(0x10Bu, t, need, 1u))) {
+            *aborted = true;
+            return 0;
+        }
+        __nanosleep(20);
+        if (polls) *polls += 1u;
+        if ((need >> lane) & 1u) own = ptx::ld_relaxed_gpu(own_ptr);
+    }
+    // ---- earlier blocks, nearest first: whole-block sums up to the nearest block whose end offset is published
+    while (true) {
+        const bool has_prefix = desc_status(pfx, epoch) == kStatusPrefix;
+        const bool complete = m < 0 || static_cast<uint32_t>(blk >> 40) == kBlockCubes;
+        const uint32_t prefix = __ballot_sync(kFullMask, has_prefix);
+        const uint32_t incomplete = __ballot_sync(kFullMask, !complete && !has_prefix);
+        const int nearest = prefix ? __ffs(prefix) - 1 : 32;
+        const uint32_t need = incomplete & (prefix ? (1u << nearest) - 1u : 0xffffffffu);
+        if (need == 0) {
+            const uint32_t mine = lane < nearest ? static_cast<uint32_t>(blk) : lane == nearest ? static_cast<uint32_t>(pfx) : 0u;
+            sum += __reduce_add_sync(kFullMask, mine);
+            if (prefix) return sum;
+            m -= 32;  // (only with more than 1024 unresolved cubes in front of t)
+            if (polls) *polls += 0x10000u;
+            blk = m >= 0 ? ptx::ld_relaxed_gpu(block_word(m)) : 0ull;
+            pfx = m >= 0 ? ptx::ld_relaxed_gpu(block_end(m)) : pack_desc(epoch, kStatusPrefix, base);
+            continue;
+        }
+        if (__any_sync(kFullMask, dog.expired(0x10Bu, t, need, 2u))) {
+            *aborted = true;
+            return 0;
+        }
+        __nanosleep(20);
+        if (polls) *polls += 1u;
+        if ((need >> lane) & 1u) {
+            blk = ptx::ld_relaxed_gpu(block_word(m));
+            pfx = ptx::ld_relaxed_gpu(block_end(m));
+        }
     }
 }
 
@@ -393,7 +470,7 @@ __global__ void __launch_bounds__(kCubeThreads)
             //      prefetch the next cube (thread 32). All are L2 round trips hidden behind phase 2.
             if (warp == 0) {
                 if (lane == 0) {
-                    ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, kStatusAggregate, cube_words));
+                    ptx::st_relaxed_gpu(a.desc + static_cast<size_t>(t) * kDescStride, pack_desc(a.epoch, kStatusAggregate, cube_words));
                 }
                 if (prev_t != kNone && prev_t != 0) {
                     sample = look_back_load(a.desc, static_cast<int64_t>(prev_t) - 1, a.epoch, lane, launch_base);
@@ -429,7 +506,7 @@ __global__ void __launch_bounds__(kCubeThreads)
             const uint32_t exclusive = prev_t == 0 ? launch_base : look_back(a.desc, prev_t, a.epoch, lane, sample, launch_base);
             if (lane == 0) {
                 const uint32_t after = exclusive + prev_words;
-                ptx::st_relaxed_gpu(a.desc + prev_t, pack_desc(a.epoch, kStatusPrefix, after));
+                ptx::st_relaxed_gpu(a.desc + static_cast<size_t>(prev_t) * kDescStride, pack_desc(a.epoch, kStatusPrefix, after));
                 aux.prefix[iter & 1] = exclusive;
                 a.out_offsets[prev_t] = after;  // "offset_after", reference src/ndzip/common.hh:342-347
                 if (prev_t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452
@@ -648,6 +725,26 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                 continue;
             }
             uint32_t *tile = slots + s * slot_words;
+            if (a.debug_flags & 4u) {
+                // profiling aid: no encoding at all, every cube "compresses" to its 128 head words (garbage). What is
+                // left is the load pipeline: tickets, TMA, slot hand-over, look-back.
+                if (u == 0) {
+                    ptx::st_relaxed_gpu(a.desc + static_cast<size_t>(t) * kDescStride, pack_desc(a.epoch, kStatusAggregate, tr::chunks));
+                    if (LB == 0) {
+                        atomicAdd(a.block_desc + static_cast<size_t>(t >> kBlockShift) * kDescStride, static_cast<unsigned long long>(block_contribution(tr::chunks)));
+                    }
+                    aux.words[s] = tr::chunks;
+                    if (Early) ptx::mbar_arrive(&aux.counted[s]);
+                }
+                ptx::mbar_arrive(&aux.done[s]);
+                ++st_n;
+                s += G;
+                if (s >= S) {
+                    s -= S;
+                    parity ^= 1u;
+                }
+                continue;
+            }
 
             // phase 1: residuals of run u, chunk head, plane count
             Bits r[32];
@@ -677,7 +774,10 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             uint32_t body = tr::chunks + before + inclusive - count;
             if constexpr (sizeof(Bits) == 8) body = __shfl_sync(kFullMask, body, lane & ~1);
             if (u == 0) {
-                ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, kStatusAggregate, cube_words));
+                ptx::st_relaxed_gpu(a.desc + static_cast<size_t>(t) * kDescStride, pack_desc(a.epoch, kStatusAggregate, cube_words));
+                if (LB == 0) {
+                    atomicAdd(a.block_desc + static_cast<size_t>(t >> kBlockShift) * kDescStride, static_cast<unsigned long long>(block_contribution(cube_words)));
+                }
                 aux.words[s] = cube_words;
                 if (Early) ptx::mbar_arrive(&aux.counted[s]);  // the retire warp resolves the cube's offset while phase 2 runs
             }
@@ -812,12 +912,16 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                 exclusive = t * static_cast<uint32_t>(tr::max_cube_words);  // profiling aid: no look-back, fixed-stride output (NOT the stream format)
             } else if (t != 0) {
                 bool aborted = false;
-                if constexpr (LB < 0) {  // windows of 32 * -LB cubes read with weak L1-bypassing loads (ld.global.cg)
+                if constexpr (LB == 0) {  // two-level look-back over blocks of 32 cubes
+                    exclusive = look_back_blocks(reinterpret_cast<const uint64_t *>(a.desc), reinterpret_cast<const uint64_t *>(a.block_desc), t, a.epoch,
+                            lane, launch_base, a.watch, &aborted, Stats ? &st_polls : nullptr);
+                } else if constexpr (LB < 0) {  // windows of 32 * -LB cubes read with weak L1-bypassing loads (ld.global.cg)
                     const look_back_window<-LB> first = look_back_load<-LB, true>(a.desc, static_cast<int64_t>(t) - 1, a.epoch, lane, launch_base);
                     exclusive = look_back<-LB, true>(a.desc, t, a.epoch, lane, first, launch_base, a.watch, &aborted, Stats ? &st_polls : nullptr);
                 } else {
-                    const look_back_window<LB> first = look_back_load<LB>(a.desc, static_cast<int64_t>(t) - 1, a.epoch, lane, launch_base);
-                    exclusive = look_back<LB>(a.desc, t, a.epoch, lane, first, launch_base, a.watch, &aborted, Stats ? &st_polls : nullptr);
+                    constexpr int D = LB > 0 ? LB : 1;
+                    const look_back_window<D> first = look_back_load<D>(a.desc, static_cast<int64_t>(t) - 1, a.epoch, lane, launch_base);
+                    exclusive = look_back<D>(a.desc, t, a.epoch, lane, first, launch_base, a.watch, &aborted, Stats ? &st_polls : nullptr);
                 }
                 if (aborted) break;
             }
@@ -825,7 +929,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             st_b += c2 - c1;
             if (lane == 0) {
                 const uint32_t after = exclusive + words;
-                ptx::st_relaxed_gpu(a.desc + t, pack_desc(a.epoch, kStatusPrefix, after));
+                ptx::st_relaxed_gpu(a.desc + static_cast<size_t>(t) * kDescStride, pack_desc(a.epoch, kStatusPrefix, after));
                 a.out_offsets[t] = after;  // "offset_after", reference src/ndzip/common.hh:342-347
                 if (t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452
                 if (t == a.count - 1) {
@@ -1259,14 +1363,13 @@ struct ws_variant {
     bool stats;
 };
 // Variant 0 is what the library uses; 1-4 are kept for A/B runs and so that the tests cover every code path (late
-// look-back, dynamic assignment, weak descriptor loads, prefetch limit + statistics). Measured on B200
-// (profiles/README.md): 5 groups + 3 retire warps is the best split for float, 3 + 2 for double; the early look-back
-// gains 4.5 % on 3-D grids and loses 1-4 % on 1-D ones; dynamic assignment gains 3 % on 3-D float and loses 6-10 %
-// elsewhere.
-constexpr ws_variant kWsVariants32[] = {{5, 3, 2, 1, 0, 2, false, false}, {5, 3, 2, 1, 0, 0, false, false}, {5, 3, 2, 1, 0, 1, true, false},
-        {4, 4, -2, 1, 0, 1, false, false}, {5, 3, 2, 1, 3, 2, false, true}};
-constexpr ws_variant kWsVariants64[] = {{3, 2, 2, 1, 0, 2, false, false}, {3, 2, 2, 1, 0, 0, false, false}, {3, 2, 2, 1, 0, 1, true, false},
-        {3, 3, -2, 1, 0, 1, false, false}, {3, 2, 2, 1, 2, 2, false, true}};
+// look-back with 64-cube windows, dynamic assignment, weak descriptor loads, prefetch limit + statistics). Measured on
+// B200 with descriptors one per 64 bytes (profiles/README.md): float 5 groups + 4 retire warps + two-level look-back
+// (3-D 0.193 ms, 1-D 0.297 ms per GiB), double 3 + 2 with 32-cube windows (2-D 0.199 ms).
+constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}, {5, 3, 2, 1, 0, 0, false, false}, {5, 4, 1, 1, 0, 1, true, false},
+        {4, 4, -2, 1, 0, 1, false, false}, {5, 4, 0, 1, 3, 1, false, true}};
+constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 2, 2, 1, 0, 0, false, false}, {3, 2, 0, 1, 0, 1, true, false},
+        {3, 3, -2, 1, 0, 1, false, false}, {3, 2, 1, 1, 2, 1, false, true}};
 constexpr int kNumWsVariants32 = sizeof(kWsVariants32) / sizeof(ws_variant);
 constexpr int kNumWsVariants64 = sizeof(kWsVariants64) / sizeof(ws_variant);
 
@@ -1320,6 +1423,10 @@ uint32_t compress_ws_ticket_overdraw(int dtype, int variant, uint32_t grid) {
     return grid * static_cast<uint32_t>(v.ticket_lookahead);  // the loader draws that many up front, then one per cube
 }
 int compress_ws_variants(int dtype) { return dtype == 0 ? kNumWsVariants32 : kNumWsVariants64; }
+bool compress_ws_uses_blocks(int dtype, int variant) {
+    if (variant < 0 || variant >= compress_ws_variants(dtype)) variant = 0;
+    return (dtype == 0 ? kWsVariants32[variant] : kWsVariants64[variant]).look_back_depth == 0;
+}
 
 cudaError_t configure_kernels(kernel_config &cfg) {
     int dev = 0;

@@ -14,6 +14,15 @@ enum class load_path : int {
     scalar = 2,  // element-wise global loads: any shape / alignment
 };
 
+// Look-back descriptors are kDescStride 64-bit words apart. Packed (stride 1), the ~200 descriptors that are live at
+// any time sit in a dozen 128-byte lines which every retire warp of every SM polls and every cube writes twice: with
+// one descriptor per 32-byte sector the kernel is 13 % faster and more retire warps start to pay, with one per 64
+// bytes another 2 % (profiles/README.md). Costs 64 instead of 8 bytes of scratch per hypercube.
+#ifndef NDZB_DESC_STRIDE
+#define NDZB_DESC_STRIDE 8
+#endif
+constexpr int kDescStride = NDZB_DESC_STRIDE;
+
 constexpr uint32_t kWatchdogWords = 8 + 6 * 4000;
 
 struct compress_launch {
@@ -29,6 +38,7 @@ struct compress_launch {
     uint32_t *length_out;      // nullable: receives length_add + total
     uint32_t length_add;
     uint64_t *desc;            // decoupled look-back descriptors, >= count entries
+    unsigned long long *block_desc;  // compress_ws_kernel, two-level look-back: one word per 32 cubes (count << 40 | sum of lengths), zeroed before the launch
     uint32_t *ticket;          // free-running ticket counter
     uint32_t ticket_base;      // value of *ticket when this launch starts
     uint32_t epoch;            // tag that invalidates descriptors of earlier launches (< 2^30)
@@ -63,6 +73,7 @@ cudaError_t launch_compress(int dtype, int dims, load_path path, const compress_
 // Warp-specialised compress kernel (TMA-compatible inputs only): one CTA per SM, `variant` < compress_ws_variants(dtype).
 uint32_t compress_ws_ticket_overdraw(int dtype, int variant, uint32_t grid);
 int compress_ws_variants(int dtype);
+bool compress_ws_uses_blocks(int dtype, int variant);  // two-level look-back: block_desc must be zeroed before the launch
 cudaError_t launch_compress_ws(int dtype, int dims, int variant, const compress_launch &args, const CUtensorMap &in_map,
         uint32_t grid, cudaStream_t stream);
 cudaError_t launch_decompress(int dtype, int dims, bool vec_store, const decompress_launch &args, uint32_t grid,
