@@ -818,8 +818,12 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
         // Tickets are drawn LA cubes ahead and kept in registers, so the ~1 us round trip of
         // the atomic is never waited for (a ticket drawn early still only ever waits for EARLIER tickets:
         // for the slot of the CTA's cube S places back, whose retirement needs lengths of earlier cubes).
-        uint32_t tk[LA];
-        {
+        // (LA == 0: the ticket is drawn only when the slot is free, right before the load is issued, and the loader waits
+        // for the atomic: no SM ever holds a ticket it cannot load yet.)
+        constexpr int kTk = LA > 0 ? LA : 1;
+        uint32_t tk[kTk];
+        bool ended = false;  // LA == 0: an out-of-range ticket has been drawn, no more draws
+        if constexpr (LA > 0) {
             const uint32_t first = atomicAdd(a.ticket, static_cast<uint32_t>(LA)) - a.ticket_base;
 #pragma unroll
             for (int j = 0; j < LA; ++j) tk[j] = first + j;
@@ -833,7 +837,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
         const long long l0 = now();
         while (poison < kPoison) {
 #pragma unroll
-            for (int j = 0; j < LA; ++j) {
+            for (int j = 0; j < kTk; ++j) {
                 if (poison == kPoison) break;
                 const long long c0 = now();
                 if (!first_round && !mbar_wait_watched(&aux.empty[s], parity, a.watch, 0xE017u, static_cast<uint32_t>(s), seq)) return;
@@ -848,9 +852,13 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                     }
                 }
                 st_b += now() - c1;
+                if constexpr (LA == 0) {
+                    if (!ended) tk[0] = atomicAdd(a.ticket, 1u) - a.ticket_base;
+                    ended = tk[0] >= a.count;
+                }
                 const uint32_t t = tk[j];
                 if (t < a.count) {
-                    tk[j] = atomicAdd(a.ticket, 1u) - a.ticket_base;
+                    if constexpr (LA > 0) tk[j] = atomicAdd(a.ticket, 1u) - a.ticket_base;
                     aux.ticket[s] = t;
                     aux.seq[s] = seq;
                     if (Stats) {
@@ -1363,11 +1371,12 @@ struct ws_variant {
     bool stats;
 };
 // Variant 0 is what the library uses; 1-4 are kept for A/B runs and so that the tests cover every code path (late
-// look-back with 64-cube windows, dynamic assignment, weak descriptor loads, prefetch limit + statistics). Measured on
+// look-back with 64-cube windows, dynamic assignment, weak descriptor loads + late ticket binding, prefetch limit +
+// statistics). Measured on
 // B200 with descriptors one per 64 bytes (profiles/README.md): float 5 groups + 4 retire warps + two-level look-back
 // (3-D 0.193 ms, 1-D 0.297 ms per GiB), double 3 + 2 with 32-cube windows (2-D 0.199 ms).
 constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}, {5, 3, 2, 1, 0, 0, false, false}, {5, 4, 1, 1, 0, 1, true, false},
-        {4, 4, -2, 1, 0, 1, false, false}, {5, 4, 0, 1, 3, 1, false, true}};
+        {4, 4, -2, 0, 0, 1, false, false}, {5, 4, 0, 1, 3, 1, false, true}};
 constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 2, 2, 1, 0, 0, false, false}, {3, 2, 0, 1, 0, 1, true, false},
         {3, 3, -2, 1, 0, 1, false, false}, {3, 2, 1, 1, 2, 1, false, true}};
 constexpr int kNumWsVariants32 = sizeof(kWsVariants32) / sizeof(ws_variant);
@@ -1420,7 +1429,7 @@ int compress_ws_variants(int dtype);
 uint32_t compress_ws_ticket_overdraw(int dtype, int variant, uint32_t grid) {
     if (variant < 0 || variant >= compress_ws_variants(dtype)) variant = 0;
     const ws_variant v = dtype == 0 ? kWsVariants32[variant] : kWsVariants64[variant];
-    return grid * static_cast<uint32_t>(v.ticket_lookahead);  // the loader draws that many up front, then one per cube
+    return grid * static_cast<uint32_t>(v.ticket_lookahead > 0 ? v.ticket_lookahead : 1);  // drawn beyond `count`: the look-ahead, or the one ticket that ends a late-binding loader
 }
 int compress_ws_variants(int dtype) { return dtype == 0 ? kNumWsVariants32 : kNumWsVariants64; }
 bool compress_ws_uses_blocks(int dtype, int variant) {
