@@ -1378,7 +1378,7 @@ struct ws_variant {
 constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}, {5, 3, 2, 1, 0, 0, false, false}, {5, 4, 1, 1, 0, 1, true, false},
         {4, 4, -2, 0, 0, 1, false, false}, {5, 4, 0, 1, 3, 1, false, true}};
 constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 2, 2, 1, 0, 0, false, false}, {3, 2, 0, 1, 0, 1, true, false},
-        {3, 3, -2, 1, 0, 1, false, false}, {3, 2, 1, 1, 2, 1, false, true}};
+        {3, 3, -2, 0, 0, 1, false, false}, {3, 2, 1, 1, 2, 1, false, true}};
 constexpr int kNumWsVariants32 = sizeof(kWsVariants32) / sizeof(ws_variant);
 constexpr int kNumWsVariants64 = sizeof(kWsVariants64) / sizeof(ws_variant);
 
