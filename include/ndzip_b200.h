@@ -41,7 +41,7 @@ typedef enum ndzb_status {
 
 /* Opaque per-stream context. Owns the scratch the reference's cuda_compressor_impl owns
  * (src/ndzip/cuda_codec.inl:536-552): here only the decoupled look-back descriptors
- * (8 bytes per hypercube) and two counters — no chunk scratch, no scan levels.
+ * (one 8-byte word per 64 bytes and hypercube) and two counters — no chunk scratch, no scan levels.
  * Not thread-safe per object, like the reference. */
 typedef struct ndzb_ctx ndzb_ctx;
 
