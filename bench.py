@@ -182,12 +182,38 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 
 def measured_hbm_peak():
+    """HBM GB/s from the driver-written MEASURED_PEAKS.json (burst figure: the roofline kernel is timed alone, one launch
+    between synchronisations), else B200_PROFILING.md's fallback. The file's schema is not ours, so any numeric entry
+    whose key path mentions hbm is accepted, preferring one that also says burst."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except (OSError, KeyError, ValueError):
+            doc = json.load(f)
+    except (OSError, ValueError):
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    found = []
+
+    def walk(node, trail):
+        if isinstance(node, dict):
+            for k, v in node.items():
+                walk(v, trail + [str(k).lower()])
+        elif isinstance(node, (int, float)) and not isinstance(node, bool):
+            key = ".".join(trail)
+            if "hbm" in key and "tf" not in key:
+                v = float(node)
+                if 500.0 < v < 20000.0:          # GB/s
+                    found.append((key, v))
+                elif 0.5 < v < 20.0:             # TB/s
+                    found.append((key, v * 1000.0))
+
+    walk(doc, [])
+    if not found:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s; no hbm entry in MEASURED_PEAKS.json)"
+    for want in ("burst", "hbm_gbs", ""):
+        for key, v in found:
+            if want in key:
+                return v, f"measured (MEASURED_PEAKS.json {key})"
+    return found[0][1], f"measured (MEASURED_PEAKS.json {found[0][0]})"
 
 
 def ncu_traffic_per_launch(workload):
