@@ -1,4 +1,6 @@
 #!/bin/bash
+# Full GPU validation of a build: smoke, every -m gpu test group, CLI tests, stress, default bench, all BASELINE
+# workloads, launch list + one ncu capture of the compress kernel. Writes gpurun_out/.
 mkdir -p gpurun_out
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/f_smoke.log 2>&1; echo "[smoke] rc=$? $(tail -1 gpurun_out/f_smoke.log)"
 bash scripts/gpu_tests.sh
