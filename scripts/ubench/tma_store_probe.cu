@@ -1,3 +1,4 @@
+// Build: nvcc -std=c++17 -O2 -gencode arch=compute_100a,code=sm_100a -o tma_store_probe tma_store_probe.cu -lcuda
 // Probe: which forms of cp.async.bulk.tensor stores of 32-bit words to a 4-byte-aligned destination are legal on
 // sm_100a? One case per process (CUDA errors are sticky).  usage: tma_store_probe <rank> <box> <x> <y> <rows_log2> [lanes]
 #include <cuda.h>
