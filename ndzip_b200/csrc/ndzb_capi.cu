@@ -96,7 +96,9 @@ struct ndzb_ctx {
     cudaStream_t stream = nullptr;
     uint32_t desc_capacity = 0;
     uint64_t *d_desc = nullptr;       // look-back descriptors
-    unsigned long long *d_blocks = nullptr;  // block-level look-back words (one per 32 cubes), same capacity as d_desc
+    unsigned long long *d_blocks[2] = {nullptr, nullptr};  // block-level look-back words (one per 32 cubes, capacity as d_desc); the two
+                                                            // arrays alternate between launches, each launch zeroes the other one
+    int blocks_cur = 0;
     uint32_t *d_counters = nullptr;   // [0] ticket counter, [1] total compressed words of the last launch
     uint32_t ticket_base = 0;
     uint32_t epoch = 1;
@@ -129,9 +131,13 @@ int ensure_descriptors(ndzb_ctx *ctx, uint32_t cubes) {
     // Growing synchronises the device (cudaFree/cudaMalloc); contexts sized by
     // compressor_requirements never get here.
     if (ctx->d_desc) NDZB_CUDA(cudaFree(ctx->d_desc));
-    if (ctx->d_blocks) NDZB_CUDA(cudaFree(ctx->d_blocks));
-    ctx->d_blocks = nullptr;
-    NDZB_CUDA(cudaMalloc(&ctx->d_blocks, (static_cast<size_t>(cubes) / 32 + 1) * kDescStride * sizeof(unsigned long long)));
+    for (auto &b : ctx->d_blocks) {
+        if (b) NDZB_CUDA(cudaFree(b));
+        b = nullptr;
+        const size_t bytes = (static_cast<size_t>(cubes) / 32 + 1) * kDescStride * sizeof(unsigned long long);
+        NDZB_CUDA(cudaMalloc(&b, bytes));
+        NDZB_CUDA(cudaMemsetAsync(b, 0, bytes, ctx->stream));
+    }
     ctx->d_desc = nullptr;
     ctx->desc_capacity = 0;
     NDZB_CUDA(cudaMalloc(&ctx->d_desc, static_cast<size_t>(cubes) * kDescStride * sizeof(uint64_t)));
@@ -194,9 +200,13 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
     a.debug_flags = ctx->ws_debug;
     a.stats = ctx->d_stats;
     if (ws) {
-        a.block_desc = ctx->d_blocks;
         if (compress_ws_uses_blocks(ctx->dtype, ctx->ws_variant)) {
-            NDZB_CUDA(cudaMemsetAsync(ctx->d_blocks, 0, (static_cast<size_t>(count) / 32 + 1) * kDescStride * sizeof(unsigned long long), ctx->stream));
+            // this launch accumulates into one array (all zero: zeroed at allocation or by the previous launch) and zeroes
+            // the other one for the next launch, whatever its cube count will be
+            a.block_desc = ctx->d_blocks[ctx->blocks_cur];
+            a.block_desc_next = ctx->d_blocks[ctx->blocks_cur ^ 1];
+            a.block_words_next = ctx->desc_capacity / 32 + 1;
+            ctx->blocks_cur ^= 1;
         }
         const cudaError_t e = launch_compress_ws(ctx->dtype, ctx->dims, ctx->ws_variant, a, map, grid, ctx->stream);
         if (e != cudaSuccess) return cuda_fail(e, "compress_ws_kernel launch");
@@ -531,7 +541,9 @@ void ndzb_ctx_destroy(ndzb_ctx *ctx) {
     if (!ctx) return;
     if (ctx->d_desc) cudaFree(ctx->d_desc);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
-    if (ctx->d_blocks) cudaFree(ctx->d_blocks);
+    for (auto b : ctx->d_blocks) {
+        if (b) cudaFree(b);
+    }
     if (ctx->d_watch) cudaFree(ctx->d_watch);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->d_in) cudaFree(ctx->d_in);

@@ -813,7 +813,16 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
         }
     } else if (warp == 4 * G) {
         // ----------------------------------------------------------------------------------- loader
-        if (lane != 0) return;
+        if (lane != 0) {
+            // The loader warp's other 31 lanes have one job: zero the block words of the NEXT launch (the two arrays
+            // alternate), which saves a memset node in front of every launch.
+            if (LB == 0 && a.block_desc_next) {
+                for (uint32_t i = blockIdx.x * 31u + static_cast<uint32_t>(lane - 1); i < a.block_words_next; i += gridDim.x * 31u) {
+                    a.block_desc_next[static_cast<size_t>(i) * kDescStride] = 0ull;
+                }
+            }
+            return;
+        }
         ptx::tma_prefetch_desc(&in_map);
         // Tickets are drawn LA cubes ahead and kept in registers, so the ~1 us round trip of
         // the atomic is never waited for (a ticket drawn early still only ever waits for EARLIER tickets:

@@ -38,7 +38,9 @@ struct compress_launch {
     uint32_t *length_out;      // nullable: receives length_add + total
     uint32_t length_add;
     uint64_t *desc;            // decoupled look-back descriptors, >= count entries
-    unsigned long long *block_desc;  // compress_ws_kernel, two-level look-back: one word per 32 cubes (count << 40 | sum of lengths), zeroed before the launch
+    unsigned long long *block_desc;  // compress_ws_kernel, two-level look-back: one word per 32 cubes (count << 40 | sum of lengths), all zero when the launch starts
+    unsigned long long *block_desc_next;  // the array the NEXT launch will use: this launch zeroes its first block_words_next words (nullable)
+    uint32_t block_words_next;
     uint32_t *ticket;          // free-running ticket counter
     uint32_t ticket_base;      // value of *ticket when this launch starts
     uint32_t epoch;            // tag that invalidates descriptors of earlier launches (< 2^30)
@@ -73,7 +75,7 @@ cudaError_t launch_compress(int dtype, int dims, load_path path, const compress_
 // Warp-specialised compress kernel (TMA-compatible inputs only): one CTA per SM, `variant` < compress_ws_variants(dtype).
 uint32_t compress_ws_ticket_overdraw(int dtype, int variant, uint32_t grid);
 int compress_ws_variants(int dtype);
-bool compress_ws_uses_blocks(int dtype, int variant);  // two-level look-back: block_desc must be zeroed before the launch
+bool compress_ws_uses_blocks(int dtype, int variant);  // two-level look-back: needs block_desc / block_desc_next
 cudaError_t launch_compress_ws(int dtype, int dims, int variant, const compress_launch &args, const CUtensorMap &in_map,
         uint32_t grid, cudaStream_t stream);
 cudaError_t launch_decompress(int dtype, int dims, bool vec_store, const decompress_launch &args, uint32_t grid,
