@@ -11,7 +11,7 @@ for wl in cfg1 cfg3 cfg4 cfg5; do
   timeout 400 python bench.py --workload $wl --steps 20 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/f_bench_$wl.json 2> gpurun_out/f_bench_$wl.err
   echo "[bench $wl] rc=$? $(python scripts/bench_summary.py gpurun_out/f_bench_$wl.json 2>/dev/null | head -3)"
 done
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r3_launches.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:compress|decompress|border|fixup|offset" -c 40 --csv --log-file gpurun_out/r3_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/f_ncu_list.log 2>&1; echo "[ncu list] rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:compress_ws -s 4 -c 1 -o gpurun_out/r3_compress_ws -f \
     python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/f_ncu_c.log 2>&1; echo "[ncu compress] rc=$?"
