@@ -220,3 +220,209 @@ def gather_global_stream(layout: ShardLayout, local_stream, fixed_header32, root
         for req in dist.batch_isend_irecv(ops):
             req.wait()
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Sharded stream container (new work, nothing to replace in the reference)
+#
+# An 8-GPU pipeline that compresses to storage and decompresses again on 8 GPUs never needs the global
+# stream: neither the cross-rank offset exchange nor the gather to one root. The container keeps every
+# rank's SELF-CONTAINED local ndzip stream (the stream of its slab, which the reference decoder can read
+# with `-n <slab shape>`) behind a small segment table:
+#
+#   u32 magic "NDZS" | u32 version | u32 dtype (0 f32, 1 f64) | u32 dims | u32 shape[3] | u32 segments
+#   per segment: u32 slab_begin | u32 slab_end (dimension 0) | u64 stream_words | u64 byte_offset
+#   segments, each starting at a multiple of 16 bytes
+#
+# Writing needs one all-gather of the stream lengths (for the byte offsets); reading needs nothing: a
+# rank takes the segments whose slabs it owns, in any world size. `to_global_stream` converts to the
+# reference's single stream when one is wanted.
+
+SHARDED_MAGIC = 0x535A444E  # "NDZS" little endian
+SHARDED_VERSION = 1
+_FIXED_WORDS = 8            # magic, version, dtype, dims, shape[3], segments
+_SEGMENT_WORDS = 6          # begin, end, words (2), offset (2)
+
+
+@dataclass
+class Segment:
+    slab: Tuple[int, int]      # [begin, end) along dimension 0 of the global grid
+    stream_words: int          # length of the slab's ndzip stream in bits_type words
+    byte_offset: int           # where it starts in the container
+
+
+@dataclass
+class ShardedHeader:
+    dtype: str
+    shape: Tuple[int, ...]
+    segments: List[Segment]
+
+    @property
+    def header_bytes(self) -> int:
+        return _align16(4 * (_FIXED_WORDS + _SEGMENT_WORDS * len(self.segments)))
+
+    @property
+    def total_bytes(self) -> int:
+        if not self.segments:
+            return self.header_bytes
+        last = self.segments[-1]
+        return last.byte_offset + last.stream_words * np.dtype(self.dtype).itemsize
+
+    def slab_shape(self, i: int) -> Tuple[int, ...]:
+        return slab_shape(self.shape, self.segments[i].slab)
+
+
+def _align16(n: int) -> int:
+    return (n + 15) // 16 * 16
+
+
+def sharded_header(dtype, global_shape: Sequence[int], stream_words: Sequence[int]) -> ShardedHeader:
+    """Segment table for `len(stream_words)` ranks that own the slabs of slab_partition()."""
+    dtype = np.dtype(dtype).name
+    item = np.dtype(dtype).itemsize
+    spans = slab_partition(global_shape, len(stream_words))
+    hdr = ShardedHeader(dtype, tuple(int(x) for x in global_shape), [])
+    offset = _align16(4 * (_FIXED_WORDS + _SEGMENT_WORDS * len(stream_words)))
+    for span, words in zip(spans, stream_words):
+        hdr.segments.append(Segment(span, int(words), offset))
+        offset = _align16(offset + int(words) * item)
+    return hdr
+
+
+def encode_sharded_header(hdr: ShardedHeader) -> bytes:
+    dims = len(hdr.shape)
+    words = [SHARDED_MAGIC, SHARDED_VERSION, 0 if hdr.dtype == "float32" else 1, dims]
+    words += list(hdr.shape) + [0] * (3 - dims) + [len(hdr.segments)]
+    for s in hdr.segments:
+        words += [s.slab[0], s.slab[1], s.stream_words & 0xffffffff, s.stream_words >> 32,
+                  s.byte_offset & 0xffffffff, s.byte_offset >> 32]
+    raw = np.asarray(words, dtype=np.uint32).tobytes()
+    return raw + b"\0" * (hdr.header_bytes - len(raw))
+
+
+def decode_sharded_header(buf) -> ShardedHeader:
+    """Parses the table at the start of a container (bytes / memoryview / uint8 array); raises ValueError on
+    anything that is not one."""
+    raw = np.frombuffer(buf, dtype=np.uint8)
+    if raw.size < 4 * _FIXED_WORDS:
+        raise ValueError("not an ndzip sharded stream: too short")
+    fixed = raw[: 4 * _FIXED_WORDS].view(np.uint32)
+    if int(fixed[0]) != SHARDED_MAGIC:
+        raise ValueError("not an ndzip sharded stream: bad magic")
+    if int(fixed[1]) != SHARDED_VERSION:
+        raise ValueError(f"unsupported sharded stream version {int(fixed[1])}")
+    dtype_code, dims, count = int(fixed[2]), int(fixed[3]), int(fixed[7])
+    if dtype_code not in (0, 1) or not 1 <= dims <= 3:
+        raise ValueError("corrupt sharded stream header")
+    need = 4 * (_FIXED_WORDS + _SEGMENT_WORDS * count)
+    if raw.size < need:
+        raise ValueError("truncated sharded stream header")
+    table = raw[4 * _FIXED_WORDS: need].view(np.uint32).reshape(count, _SEGMENT_WORDS)
+    hdr = ShardedHeader("float32" if dtype_code == 0 else "float64", tuple(int(x) for x in fixed[4: 4 + dims]), [])
+    end_of_previous = 0
+    for row in table:
+        seg = Segment((int(row[0]), int(row[1])), int(row[2]) | (int(row[3]) << 32), int(row[4]) | (int(row[5]) << 32))
+        if seg.slab[0] != end_of_previous or seg.slab[1] < seg.slab[0] or seg.byte_offset % 16:
+            raise ValueError("corrupt sharded stream segment table")
+        end_of_previous = seg.slab[1]
+        hdr.segments.append(seg)
+    if count and end_of_previous != hdr.shape[0]:
+        raise ValueError("sharded stream segments do not cover the grid")
+    return hdr
+
+
+def pack_sharded(dtype, global_shape: Sequence[int], local_streams: Sequence[np.ndarray]) -> bytes:
+    """One process has every rank's local stream (numpy, bits dtype): the whole container."""
+    bits = np.uint32 if np.dtype(dtype).itemsize == 4 else np.uint64
+    hdr = sharded_header(dtype, global_shape, [np.asarray(s).size for s in local_streams])
+    out = bytearray(hdr.total_bytes)
+    out[: hdr.header_bytes] = encode_sharded_header(hdr)
+    for seg, s in zip(hdr.segments, local_streams):
+        raw = np.ascontiguousarray(s, dtype=bits).tobytes()
+        out[seg.byte_offset: seg.byte_offset + len(raw)] = raw
+    return bytes(out)
+
+
+def sharded_segment(buf, hdr: ShardedHeader, i: int) -> np.ndarray:
+    """Segment i of a container as an array of bits_type words (a view into `buf`)."""
+    bits = np.uint32 if hdr.dtype == "float32" else np.uint64
+    seg = hdr.segments[i]
+    raw = np.frombuffer(buf, dtype=np.uint8)
+    end = seg.byte_offset + seg.stream_words * np.dtype(bits).itemsize
+    if end > raw.size:
+        raise ValueError("truncated sharded stream")
+    return raw[seg.byte_offset: end].view(bits)
+
+
+def segments_of_rank(hdr: ShardedHeader, rank: int, world_size: int) -> List[int]:
+    """Which segments a rank of a (possibly different) world size decodes: contiguous, as even as possible."""
+    n = len(hdr.segments)
+    lo = rank * n // world_size
+    hi = (rank + 1) * n // world_size
+    return list(range(lo, hi))
+
+
+def to_global_stream(buf) -> np.ndarray:
+    """The reference's single stream of the whole grid, from a container whose slabs are those of
+    slab_partition(shape, segments) (what write_sharded / pack_sharded produce)."""
+    hdr = decode_sharded_header(buf)
+    spans = slab_partition(hdr.shape, len(hdr.segments))
+    if [s.slab for s in hdr.segments] != spans:
+        raise ValueError("segments are not the slabs of slab_partition(); decode them one by one instead")
+    return stitch_global_stream(hdr.dtype, hdr.shape, [sharded_segment(buf, hdr, i) for i in range(len(hdr.segments))])
+
+
+def write_sharded(path: str, dtype, global_shape: Sequence[int], local_stream, group=None) -> ShardedHeader:
+    """Collective: every rank writes its own segment of the container at `path` (a file all ranks can reach).
+    `local_stream`: the rank's complete local stream (numpy bits array, or a torch tensor on any device — it is
+    brought to the host here). The only communication is one all-gather of the stream lengths."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if isinstance(local_stream, torch.Tensor):
+        host = local_stream.detach().cpu().numpy()
+        device = local_stream.device if local_stream.is_cuda else "cpu"
+    else:
+        host = np.ascontiguousarray(local_stream)
+        device = "cpu"
+    mine = torch.tensor([int(host.size)], dtype=torch.int64, device=device)
+    if world > 1:
+        gathered = torch.empty(world, dtype=torch.int64, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+    else:
+        gathered = mine
+    hdr = sharded_header(dtype, global_shape, [int(w) for w in gathered.cpu().tolist()])
+    if rank == 0:
+        with open(path, "wb") as f:
+            f.write(encode_sharded_header(hdr))
+            f.truncate(hdr.total_bytes)
+    if world > 1:
+        dist.barrier(group=group)
+    seg = hdr.segments[rank]
+    with open(path, "r+b") as f:
+        f.seek(seg.byte_offset)
+        f.write(host.tobytes())
+    if world > 1:
+        dist.barrier(group=group)
+    return hdr
+
+
+def read_sharded(path: str, rank: int = 0, world_size: int = 1):
+    """The segments a rank owns: [(slab span, slab shape, stream words as numpy bits array), ...]. No communication."""
+    with open(path, "rb") as f:
+        head = f.read(4 * _FIXED_WORDS)
+        count = int(np.frombuffer(head, dtype=np.uint32)[7]) if len(head) == 4 * _FIXED_WORDS else 0
+        head += f.read(4 * _SEGMENT_WORDS * count)
+        hdr = decode_sharded_header(head)
+        bits = np.uint32 if hdr.dtype == "float32" else np.uint64
+        out = []
+        for i in segments_of_rank(hdr, rank, world_size):
+            seg = hdr.segments[i]
+            f.seek(seg.byte_offset)
+            raw = f.read(seg.stream_words * np.dtype(bits).itemsize)
+            if len(raw) != seg.stream_words * np.dtype(bits).itemsize:
+                raise ValueError("truncated sharded stream")
+            out.append((seg.slab, hdr.slab_shape(i), np.frombuffer(raw, dtype=bits)))
+    return hdr, out

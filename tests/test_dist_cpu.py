@@ -90,3 +90,79 @@ def test_gloo_offset_exchange_and_gather(oracle, tmp_path, dtype, shape, world):
     bits = np.uint32 if dtype == "float32" else np.uint64
     expect = oracle.compress(synth.hashed(shape, dtype, seed=31))
     assert np.array_equal(got.view(bits), expect)
+
+
+# ---- sharded stream container -------------------------------------------------------------------
+
+@pytest.mark.parametrize("dtype,shape", CASES)
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_sharded_container_round_trip_and_global_stream(oracle, dtype, shape, world):
+    data = synth.hashed(shape, dtype, seed=32)
+    spans = nzd.slab_partition(shape, world)
+    local = [oracle.compress(np.ascontiguousarray(data[b:e])) for b, e in spans]
+    buf = nzd.pack_sharded(dtype, shape, local)
+    hdr = nzd.decode_sharded_header(buf)
+    assert hdr.dtype == dtype and hdr.shape == tuple(shape) and len(hdr.segments) == world
+    assert hdr.total_bytes == len(buf) and all(s.byte_offset % 16 == 0 for s in hdr.segments)
+    for i, (b, e) in enumerate(spans):  # every segment is a self-contained stream of its slab
+        assert hdr.segments[i].slab == (b, e)
+        back, consumed = oracle.decompress(nzd.sharded_segment(buf, hdr, i), dtype, hdr.slab_shape(i))
+        assert consumed == hdr.segments[i].stream_words and back.tobytes() == data[b:e].tobytes()
+    assert np.array_equal(nzd.to_global_stream(buf), oracle.compress(data))  # the reference's single stream
+
+
+def test_sharded_container_rejects_garbage(oracle):
+    data = synth.hashed((200, 130), "float32", seed=1)
+    buf = bytearray(nzd.pack_sharded("float32", data.shape, [oracle.compress(data)]))
+    for bad in (b"", bytes(64), bytes(buf[:20])):
+        with pytest.raises(ValueError):
+            nzd.decode_sharded_header(bad)
+    buf[4] = 9  # version
+    with pytest.raises(ValueError):
+        nzd.decode_sharded_header(bytes(buf))
+    good = nzd.pack_sharded("float32", data.shape, [oracle.compress(data)])
+    hdr = nzd.decode_sharded_header(good)
+    with pytest.raises(ValueError):
+        nzd.sharded_segment(good[:-8], hdr, 0)
+    assert [nzd.segments_of_rank(nzd.sharded_header("float32", (4096 * 8,), [1] * 8), r, 3) for r in range(3)] == [[0, 1], [2, 3, 4], [5, 6, 7]]
+
+
+def _container_worker(rank, world, port, dtype, shape, path):
+    import torch.distributed as dist
+    from oracle import get_oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        oracle = get_oracle()
+        data = synth.hashed(shape, dtype, seed=33)
+        b, e = nzd.slab_partition(shape, world)[rank]
+        nzd.write_sharded(path, dtype, shape, oracle.compress(np.ascontiguousarray(data[b:e])))
+        # read back with the SAME world size: exactly the own slab, no communication
+        hdr, mine = nzd.read_sharded(path, rank, world)
+        assert len(mine) == 1 and mine[0][0] == (b, e)
+        back, _ = oracle.decompress(mine[0][2], dtype, mine[0][1])
+        assert back.tobytes() == data[b:e].tobytes()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype,shape", CASES[:3])
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_sharded_write_then_read_with_any_world_size(oracle, tmp_path, dtype, shape, world):
+    import torch.multiprocessing as mp
+    path = str(tmp_path / "grid.ndzs")
+    mp.spawn(_container_worker, args=(world, _free_port(), dtype, shape, path), nprocs=world, join=True)
+    data = synth.hashed(shape, dtype, seed=33)
+    raw = open(path, "rb").read()
+    assert np.array_equal(nzd.to_global_stream(raw), oracle.compress(data))
+    # a reader with a different world size takes several (or no) segments per rank; together they cover the grid
+    for readers in (1, 2, 5):
+        rows = 0
+        for r in range(readers):
+            hdr, segs = nzd.read_sharded(path, r, readers)
+            for (b, e), slab_shape, words in segs:
+                back, _ = oracle.decompress(words, dtype, slab_shape)
+                assert back.tobytes() == data[b:e].tobytes()
+                rows += e - b
+        assert rows == shape[0]

@@ -515,3 +515,21 @@ def test_large_configs_properties(nz, oracle, dtype, shape):
     torch.cuda.synchronize()
     assert int(d_len.cpu().numpy().view(np.uint32)[0]) == n
     assert torch.equal(d_stream[:n], d_stream2[:n])
+
+
+@pytest.mark.parametrize("dtype,shape", [("float32", (96, 64, 80)), ("float64", (300, 200)), ("float32", (9 * 4096 + 77,))])
+def test_sharded_container_of_gpu_streams(nz, dtype, shape):
+    # every "rank" (here: one GPU, slab after slab) compresses its slab into a self-contained stream;
+    # the container needs no offset exchange and no gather, and converts to the single-GPU stream bit for bit
+    from gpu_util import gpu_compress, gpu_decompress
+    from ndzip_b200 import dist as nzd
+    data = synth.smooth(shape, dtype, seed=13)
+    spans = nzd.slab_partition(shape, 3)
+    local = [gpu_compress(np.ascontiguousarray(data[b:e]))[0] for b, e in spans]
+    buf = nzd.pack_sharded(dtype, shape, local)
+    hdr = nzd.decode_sharded_header(buf)
+    for i, (b, e) in enumerate(spans):
+        back = gpu_decompress(nzd.sharded_segment(buf, hdr, i), dtype, hdr.slab_shape(i))
+        assert back.tobytes() == data[b:e].tobytes()
+    whole, _ = gpu_compress(data)
+    assert np.array_equal(nzd.to_global_stream(buf), whole)
