@@ -548,12 +548,15 @@ __global__ void __launch_bounds__(kCubeThreads)
 //                             publish the cube length -> transpose + compaction into the cube image, in
 //                             place over the input tile                                     -> done[s]
 //   retire  (R warps; warp r takes cubes r, r+R, ...)
-//                             done[s] -> decoupled look-back -> header entry -> coalesced copy of the image
+//                             counted[s] (the cube's length is published; done[s] in the "late" variants) ->
+//                             decoupled look-back -> header entry -> done[s] -> coalesced copy of the image
 //                             from the slot to its final stream position                   -> empty[s]
 //
 // Against compress_kernel (3 slots per 4 warps, everything done by the same 4 warps): the pooled ring
-// feeds 6 instead of 4 encoder groups per SM from the same shared memory, and the look-back latency and
-// the copy-out land on warps that have nothing else to do.
+// feeds 5 instead of 4 encoder groups per SM from the same shared memory, and the look-back latency (an L2
+// round trip of ~1000 cycles or several, while the kernel runs) and the copy-out land on warps that have
+// nothing else to do; the look-back overlaps phase 2 of the cube. Defaults (kWsVariants*): float 5 groups + 4
+// retire warps, double 3 + 2.
 //
 // The copy-out is done by the retire warp's own loads and stores because a cube's destination is only
 // 4-byte aligned (the stream format packs cubes word by word): cp.async.bulk needs 16-byte alignment, and
@@ -562,9 +565,10 @@ __global__ void __launch_bounds__(kCubeThreads)
 // sm_100a, while the same box at an aligned coordinate stores correctly (scripts/ubench/tma_store_probe.cu,
 // results in profiles/README.md).
 //
-// Deadlock freedom: a ticket is only drawn for a slot that is free, its TMA load is issued at once, and
-// the groups take the CTA's cubes in ticket order; publishing a cube's length therefore never depends on
-// a later ticket, and a look-back only waits for the lengths of earlier tickets.
+// Deadlock freedom: tickets are drawn in the order in which the CTA loads and its groups encode its cubes, a
+// drawn ticket only ever waits for a slot whose release needs lengths of EARLIER tickets, and encoding never
+// waits for anything but its tile; so the smallest ticket whose length is not published yet can always make
+// progress, and a look-back only waits for lengths of earlier tickets.
 
 constexpr uint32_t kNoTicket = 0xffffffffu;
 
