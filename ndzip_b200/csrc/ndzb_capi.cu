@@ -487,8 +487,10 @@ int ndzb_ctx_create(ndzb_ctx **out_ctx, int dtype, int dims, uint32_t max_hyperc
         else if (!strcmp(p, "vec16")) ctx->forced_path = 1;
         else if (!strcmp(p, "scalar")) ctx->forced_path = 2;
     }
-    if (const char *p = getenv("NDZB_COMPRESS_KERNEL")) ctx->use_ws = strcmp(p, "v1") != 0;
-    if (const char *p = getenv("NDZB_WS_VARIANT")) ctx->ws_variant = atoi(p);
+    if (tuning_build()) {  // -DNDZB_TUNING builds only: A/B kernels and variants
+        if (const char *p = getenv("NDZB_COMPRESS_KERNEL")) ctx->use_ws = strcmp(p, "v1") != 0;
+        if (const char *p = getenv("NDZB_WS_VARIANT")) ctx->ws_variant = atoi(p);
+    }
     if (const char *p = getenv("NDZB_DEC_CTAS")) ctx->dec_ctas_cap = atoi(p);
     auto fail = [&](int rc) {
         ndzb_ctx_destroy(ctx);
@@ -499,9 +501,9 @@ int ndzb_ctx_create(ndzb_ctx **out_ctx, int dtype, int dims, uint32_t max_hyperc
     e = cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint32_t), ctx->stream);
     if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMemsetAsync counters"));
     if (const char *p = getenv("NDZB_WS_CHECK")) ctx->ws_check = atoi(p) != 0;
-    if (const char *p = getenv("NDZB_WS_DEBUG")) ctx->ws_debug = static_cast<uint32_t>(atoi(p));
+    if (const char *p = getenv("NDZB_WS_DEBUG")) ctx->ws_debug = tuning_build() ? static_cast<uint32_t>(atoi(p)) : 0u;
     if (const char *p = getenv("NDZB_WS_STATS")) {
-        if (atoi(p) != 0) {
+        if (tuning_build() && atoi(p) != 0) {
             e = cudaMalloc(&ctx->d_stats, 16 * sizeof(unsigned long long));
             if (e == cudaSuccess) e = cudaMemset(ctx->d_stats, 0, 16 * sizeof(unsigned long long));
             if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc stats"));
@@ -790,7 +792,7 @@ const char *ndzb_strerror(int status) {
 
 const char *ndzb_last_cuda_error(void) { return g_cuda_error; }
 
-const char *ndzb_version(void) { return "ndzip_b200 0.1 sm_100a"; }
+const char *ndzb_version(void) { return tuning_build() ? "ndzip_b200 0.2 sm_100a tuning" : "ndzip_b200 0.2 sm_100a"; }
 
 uint32_t ndzb_last_launch_count(const ndzb_ctx *ctx) { return ctx ? ctx->last_launches : 0; }
 

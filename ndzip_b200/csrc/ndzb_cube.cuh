@@ -75,12 +75,33 @@ NDZB_HD uint32_t rotr1(uint32_t v) {
 }
 NDZB_HD uint64_t rotr1(uint64_t v) { return (v >> 1) | (v << 63); }
 
-// reference src/ndzip/common.hh:446-449 — branch-free: xor with (sign ? 0x7f..f : 0)
+// reference src/ndzip/common.hh:446-449: negative values have their lower bits flipped, v ^ (sign ? 0x7f..f : 0).
+// For a negative v that is 0x7f..f - v = v * -1 + 0x7f..f. On the device: a sign test (alu pipe) plus a PREDICATED
+// multiply-add (fma pipe) instead of shift + xor (two alu-pipe slots per value) — the alu pipe is what bounds both
+// kernels (scripts/ubench/pipes.cu; profiles/README.md round 2). The two constants are read from constant memory
+// because ptxas folds literal ones back into an alu-pipe IADD3.
+#if defined(__CUDACC__)
+static __constant__ uint32_t kFmaPipeConsts[2] = {0xffffffffu, 0x7fffffffu};
+#endif
 NDZB_HD uint32_t complement_negative(uint32_t v) {
+#if defined(__CUDA_ARCH__) && !defined(NDZB_COMPLEMENT_XOR)
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %0, 0;\n\t@p mad.lo.s32 %0, %0, %1, %2;\n\t}"
+            : "+r"(v) : "r"(kFmaPipeConsts[0]), "r"(kFmaPipeConsts[1]));
+    return v;
+#else
     return v ^ (static_cast<uint32_t>(static_cast<int32_t>(v) >> 31) & 0x7fffffffu);
+#endif
 }
 NDZB_HD uint64_t complement_negative(uint64_t v) {
+#if defined(__CUDA_ARCH__) && !defined(NDZB_COMPLEMENT_XOR)
+    uint32_t lo = static_cast<uint32_t>(v), hi = static_cast<uint32_t>(v >> 32);
+    // low word: ~lo = lo * -1 + -1; high word: hi * -1 + 0x7fffffff (a bitwise xor: no borrow between the halves)
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, 0;\n\t@p mad.lo.s32 %0, %0, %2, %2;\n\t@p mad.lo.s32 %1, %1, %2, %3;\n\t}"
+            : "+r"(lo), "+r"(hi) : "r"(kFmaPipeConsts[0]), "r"(kFmaPipeConsts[1]));
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+#else
     return v ^ (static_cast<uint64_t>(static_cast<int64_t>(v) >> 63) & 0x7fffffffffffffffull);
+#endif
 }
 
 NDZB_HD int popc32(uint32_t v) {
@@ -89,6 +110,31 @@ NDZB_HD int popc32(uint32_t v) {
 #else
     return __builtin_popcount(v);
 #endif
+}
+
+// number of leading zero bits (32 / 64 for v == 0)
+NDZB_HD int clz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __clz(static_cast<int>(v));
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
+NDZB_HD int clz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __clzll(static_cast<long long>(v));
+#else
+    return v ? __builtin_clzll(v) : 64;
+#endif
+}
+// true when the set bits of v form ONE run (or v == 0): filling the trailing zeros gives 2^k - 1
+NDZB_HD bool one_run_of_ones(uint32_t v) {
+    const uint32_t t = v | (v - 1u);
+    return (t & (t + 1u)) == 0u;
+}
+NDZB_HD bool one_run_of_ones(uint64_t v) {
+    const uint64_t t = v | (v - 1ull);
+    return (t & (t + 1ull)) == 0ull;
 }
 
 NDZB_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t sel) {
@@ -102,10 +148,34 @@ NDZB_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t sel) {
 #endif
 }
 
+// m ? a : b, bit by bit — ONE LOP3 (lut 0xE4). Written as (x & m) | (y & ~m) the compiler sees two different
+// constants and emits two LOP3 per output word (96 extra instructions per 32x32 transpose, 3 per element:
+// profiles/README.md, round 2).
+NDZB_HD uint32_t bitselect(uint32_t m, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+#else
+    return b ^ ((a ^ b) & m);
+#endif
+}
+
 // In-register 32x32 bit-matrix transpose, LSB-indexed: afterwards bit b of a[k] is what bit k of
 // a[b] was. Five butterfly stages; the 16- and 8-bit stages are byte permutes (1 PRMT per word),
 // the 4/2/1-bit stages are shift + bit-select (2 ops per word). 256 ALU ops per 1024 bits, versus
 // 32 ballots + 32 predicate set-ups PER CHUNK for a ballot transpose.
+template<int S, uint32_t M>
+NDZB_HD void butterfly_stage(uint32_t *a) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        if (k & S) continue;
+        const uint32_t x = a[k], y = a[k + S];
+        a[k] = bitselect(M, x, y << S);              // (x & M) | ((y << S) & ~M)
+        a[k + S] = bitselect(M, x >> S, y);           // ((x >> S) & M) | (y & ~M)
+    }
+}
+
 NDZB_HD void transpose32(uint32_t *a) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -120,27 +190,9 @@ NDZB_HD void transpose32(uint32_t *a) {
         a[k] = byte_perm(x, y, 0x6240);        // even bytes
         a[k + 8] = byte_perm(x, y, 0x7351);    // odd bytes
     }
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        if (k & 4) continue;
-        const uint32_t x = a[k], y = a[k + 4];
-        a[k] = (x & 0x0f0f0f0fu) | ((y << 4) & 0xf0f0f0f0u);
-        a[k + 4] = ((x >> 4) & 0x0f0f0f0fu) | (y & 0xf0f0f0f0u);
-    }
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        if (k & 2) continue;
-        const uint32_t x = a[k], y = a[k + 2];
-        a[k] = (x & 0x33333333u) | ((y << 2) & 0xccccccccu);
-        a[k + 2] = ((x >> 2) & 0x33333333u) | (y & 0xccccccccu);
-    }
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        if (k & 1) continue;
-        const uint32_t x = a[k], y = a[k + 1];
-        a[k] = (x & 0x55555555u) | ((y << 1) & 0xaaaaaaaau);
-        a[k + 1] = ((x >> 1) & 0x55555555u) | (y & 0xaaaaaaaau);
-    }
+    butterfly_stage<4, 0x0f0f0f0fu>(a);
+    butterfly_stage<2, 0x33333333u>(a);
+    butterfly_stage<1, 0x55555555u>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -377,13 +429,26 @@ NDZB_HD uint64_t planes_of_run(const uint64_t *r, uint32_t *planes_hi, uint32_t 
 // plane inside the cube (C + exclusive plane count). Three issue slots per plane (test, predicated
 // store, predicated increment) instead of a warp-per-chunk pass over all 4096 plane slots.
 
+// Fast path: the head's set bits form one run (leading zero planes, then non-zero planes down to an optional block
+// of trailing zero planes — what smooth floating-point data produces almost always): plane i then lands at slot
+// i - clz(head), so every store has a compile-time offset from one base register: ONE predicated STS per plane and
+// no dependent pointer chain. Heads with holes take the general path (test, predicated store, predicated increment).
+
 // float: image is an array of 32-bit words
 NDZB_HD void compact_planes(uint32_t *image, int chunk, uint32_t head, uint32_t body, const uint32_t *planes) {
     image[chunk] = head;
     uint32_t *out = image + body;
+    if (one_run_of_ones(head)) {
+        uint32_t *base = out - clz32(head);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        if ((head >> (31 - i)) & 1u) *out++ = planes[i];
+        for (int i = 0; i < 32; ++i) {
+            if ((head >> (31 - i)) & 1u) base[i] = planes[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if ((head >> (31 - i)) & 1u) *out++ = planes[i];
+        }
     }
 }
 
@@ -394,18 +459,30 @@ NDZB_HD void compact_planes(uint32_t *image, int chunk, bool first, uint64_t hea
     const uint32_t head_hi = static_cast<uint32_t>(head >> 32), head_lo = static_cast<uint32_t>(head);
     image[2 * chunk + (first ? 1 : 0)] = first ? head_hi : head_lo;
     uint32_t *out = image + 2 * body + (first ? 1 : 0);
+    if (one_run_of_ones(head)) {
+        uint32_t *base = out - 2 * clz64(head);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        if ((head_hi >> (31 - i)) & 1u) {
-            *out = planes_hi[i];
-            out += 2;
+        for (int i = 0; i < 32; ++i) {
+            if ((head_hi >> (31 - i)) & 1u) base[2 * i] = planes_hi[i];
         }
-    }
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        if ((head_lo >> (31 - i)) & 1u) {
-            *out = planes_lo[i];
-            out += 2;
+        for (int i = 0; i < 32; ++i) {
+            if ((head_lo >> (31 - i)) & 1u) base[64 + 2 * i] = planes_lo[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if ((head_hi >> (31 - i)) & 1u) {
+                *out = planes_hi[i];
+                out += 2;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if ((head_lo >> (31 - i)) & 1u) {
+                *out = planes_lo[i];
+                out += 2;
+            }
         }
     }
 }
@@ -418,11 +495,21 @@ NDZB_HD void compact_planes(uint32_t *image, int chunk, bool first, uint64_t hea
 NDZB_HD void run_of_image(const uint32_t *image, uint32_t head, uint32_t body, uint32_t *r) {
     uint32_t a[32];
     const uint32_t *in = image + body;
+    if (one_run_of_ones(head)) {  // see compact_planes: plane i sits at slot i - clz(head); independent loads
+        const uint32_t *base = in - clz32(head);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        uint32_t v = 0;
-        if ((head >> (31 - i)) & 1u) v = *in++;
-        a[31 - i] = v;
+        for (int i = 0; i < 32; ++i) {
+            uint32_t v = 0;
+            if ((head >> (31 - i)) & 1u) v = base[i];
+            a[31 - i] = v;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            uint32_t v = 0;
+            if ((head >> (31 - i)) & 1u) v = *in++;
+            a[31 - i] = v;
+        }
     }
     transpose32(a);
 #pragma unroll
@@ -433,23 +520,39 @@ NDZB_HD void run_of_image(const uint32_t *image, bool first, uint64_t head, uint
     const uint32_t head_hi = static_cast<uint32_t>(head >> 32), head_lo = static_cast<uint32_t>(head);
     uint32_t a[32], b[32];
     const uint32_t *in = image + 2 * body + (first ? 1 : 0);
+    if (one_run_of_ones(head)) {
+        const uint32_t *base = in - 2 * clz64(head);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        uint32_t v = 0;
-        if ((head_hi >> (31 - i)) & 1u) {
-            v = *in;
-            in += 2;
+        for (int i = 0; i < 32; ++i) {
+            uint32_t v = 0;
+            if ((head_hi >> (31 - i)) & 1u) v = base[2 * i];
+            a[31 - i] = v;
         }
-        a[31 - i] = v;
-    }
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        uint32_t v = 0;
-        if ((head_lo >> (31 - i)) & 1u) {
-            v = *in;
-            in += 2;
+        for (int i = 0; i < 32; ++i) {
+            uint32_t v = 0;
+            if ((head_lo >> (31 - i)) & 1u) v = base[64 + 2 * i];
+            b[31 - i] = v;
         }
-        b[31 - i] = v;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            uint32_t v = 0;
+            if ((head_hi >> (31 - i)) & 1u) {
+                v = *in;
+                in += 2;
+            }
+            a[31 - i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            uint32_t v = 0;
+            if ((head_lo >> (31 - i)) & 1u) {
+                v = *in;
+                in += 2;
+            }
+            b[31 - i] = v;
+        }
     }
     transpose32(a);
     transpose32(b);

@@ -19,6 +19,14 @@ namespace ndzb {
 namespace {
 
 constexpr uint32_t kFullMask = 0xffffffffu;
+// -DNDZB_TUNING builds the A/B scaffolding: tuning variants 1-4 of compress_ws_kernel, its Stats instantiation, the
+// NDZB_WS_DEBUG profiling aids (which emit INVALID streams) and compress_kernel for TMA inputs. The default build
+// carries one compress_ws_kernel per profile and none of the debug branches.
+#if defined(NDZB_TUNING)
+constexpr bool kTuning = true;
+#else
+constexpr bool kTuning = false;
+#endif
 constexpr int kSlots = 3;   // cube tiles per CTA: being copied out / being encoded / being loaded by TMA
 constexpr int kWarps = kCubeThreads / 32;
 
@@ -729,7 +737,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                 continue;
             }
             uint32_t *tile = slots + s * slot_words;
-            if (a.debug_flags & 4u) {
+            if (kTuning && (a.debug_flags & 4u)) {
                 // profiling aid: no encoding at all, every cube "compresses" to its 128 head words (garbage). What is
                 // left is the load pipeline: tickets, TMA, slot hand-over, look-back.
                 if (u == 0) {
@@ -929,7 +937,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             }
             const uint32_t words = aux.words[s];
             uint32_t exclusive = launch_base;
-            if (a.debug_flags & 2u) {
+            if (kTuning && (a.debug_flags & 2u)) {
                 exclusive = t * static_cast<uint32_t>(tr::max_cube_words);  // profiling aid: no look-back, fixed-stride output (NOT the stream format)
             } else if (t != 0) {
                 bool aborted = false;
@@ -966,7 +974,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                 st_d += c3 - c2;
             }
             // image -> stream
-            if (!(a.debug_flags & 1u)) {  // (profiling aid: bit 0 skips the copy)
+            if (!(kTuning && (a.debug_flags & 1u))) {  // (profiling aid: bit 0 skips the copy)
                 constexpr uint32_t w32 = sizeof(Bits) / 4;
                 copy_image_out(slots + s * slot_words, reinterpret_cast<uint32_t *>(out_cubes + exclusive), words * w32, lane);
             }
@@ -1349,7 +1357,11 @@ using decompress_fn = void (*)(const decompress_launch);
 template<typename Bits, int Dims>
 compress_fn compress_for(load_path p) {
     switch (p) {
+#if defined(NDZB_TUNING)
         case load_path::tma: return compress_kernel<Bits, Dims, load_path::tma>;
+#else
+        case load_path::tma: return nullptr;  // TMA-compatible inputs always take compress_ws_kernel
+#endif
         case load_path::vec16: return compress_kernel<Bits, Dims, load_path::vec16>;
         default: return compress_kernel<Bits, Dims, load_path::scalar>;
     }
@@ -1388,10 +1400,15 @@ struct ws_variant {
 // statistics). Measured on
 // B200 with descriptors one per 64 bytes (profiles/README.md): float 5 groups + 4 retire warps + two-level look-back
 // (3-D 0.193 ms, 1-D 0.297 ms per GiB), double 3 + 2 with 32-cube windows (2-D 0.199 ms).
+#if defined(NDZB_TUNING)
 constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}, {5, 3, 2, 1, 0, 0, false, false}, {5, 4, 1, 1, 0, 1, true, false},
         {4, 4, -2, 0, 0, 1, false, false}, {5, 4, 0, 1, 3, 1, false, true}};
 constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 2, 2, 1, 0, 0, false, false}, {3, 2, 0, 1, 0, 1, true, false},
         {3, 3, -2, 0, 0, 1, false, false}, {3, 2, 1, 1, 2, 1, false, true}};
+#else
+constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}};
+constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}};
+#endif
 constexpr int kNumWsVariants32 = sizeof(kWsVariants32) / sizeof(ws_variant);
 constexpr int kNumWsVariants64 = sizeof(kWsVariants64) / sizeof(ws_variant);
 
@@ -1410,13 +1427,17 @@ compress_ws_fn compress_ws_variant_fn() {
 
 template<typename Bits, int Dims>
 compress_ws_fn compress_ws_for(int variant) {
+#if defined(NDZB_TUNING)
     switch (variant) {
         case 1: return compress_ws_variant_fn<Bits, Dims, 1>();
         case 2: return compress_ws_variant_fn<Bits, Dims, 2>();
         case 3: return compress_ws_variant_fn<Bits, Dims, 3>();
         case 4: return compress_ws_variant_fn<Bits, Dims, 4>();
-        default: return compress_ws_variant_fn<Bits, Dims, 0>();
+        default: break;
     }
+#endif
+    (void) variant;
+    return compress_ws_variant_fn<Bits, Dims, 0>();
 }
 compress_ws_fn compress_ws_entry(int dtype, int dims, int variant) {
     if (dtype == 0) {
@@ -1445,6 +1466,7 @@ uint32_t compress_ws_ticket_overdraw(int dtype, int variant, uint32_t grid) {
     return grid * static_cast<uint32_t>(v.ticket_lookahead > 0 ? v.ticket_lookahead : 1);  // drawn beyond `count`: the look-ahead, or the one ticket that ends a late-binding loader
 }
 int compress_ws_variants(int dtype) { return dtype == 0 ? kNumWsVariants32 : kNumWsVariants64; }
+bool tuning_build() { return kTuning; }
 bool compress_ws_uses_blocks(int dtype, int variant) {
     if (variant < 0 || variant >= compress_ws_variants(dtype)) variant = 0;
     return (dtype == 0 ? kWsVariants32[variant] : kWsVariants64[variant]).look_back_depth == 0;
@@ -1460,6 +1482,7 @@ cudaError_t configure_kernels(kernel_config &cfg) {
         for (int dims = 1; dims <= 3; ++dims) {
             for (int p = 0; p < 3; ++p) {
                 auto fn = compress_entry(dtype, dims, static_cast<load_path>(p));
+                if (!fn) continue;
                 err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(compress_smem(dtype)));
                 if (err != cudaSuccess) return err;
                 err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
@@ -1487,6 +1510,7 @@ cudaError_t configure_kernels(kernel_config &cfg) {
 cudaError_t launch_compress(int dtype, int dims, load_path path, const compress_launch &args, const CUtensorMap *tmap,
         uint32_t grid, cudaStream_t stream) {
     static const CUtensorMap dummy{};
+    if (!compress_entry(dtype, dims, path)) return cudaErrorInvalidDeviceFunction;
     compress_entry(dtype, dims, path)<<<grid, kCubeThreads, compress_smem(dtype), stream>>>(args, tmap ? *tmap : dummy);
     return cudaGetLastError();
 }

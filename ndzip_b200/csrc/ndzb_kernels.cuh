@@ -75,6 +75,7 @@ cudaError_t launch_compress(int dtype, int dims, load_path path, const compress_
 // Warp-specialised compress kernel (TMA-compatible inputs only): one CTA per SM, `variant` < compress_ws_variants(dtype).
 uint32_t compress_ws_ticket_overdraw(int dtype, int variant, uint32_t grid);
 int compress_ws_variants(int dtype);
+bool tuning_build();  // compiled with -DNDZB_TUNING (variants 1-4, statistics, debug aids, compress_kernel for TMA inputs)
 bool compress_ws_uses_blocks(int dtype, int variant);  // two-level look-back: needs block_desc / block_desc_next
 cudaError_t launch_compress_ws(int dtype, int dims, int variant, const compress_launch &args, const CUtensorMap &in_map,
         uint32_t grid, cudaStream_t stream);

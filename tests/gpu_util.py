@@ -27,7 +27,13 @@ def load_path(name):
 @contextmanager
 def compress_kernel(kind=None, variant=None):
     """Select the compress kernel for TMA-compatible inputs (read by ndzb_ctx_create):
-    kind "v1" = compress_kernel, anything else = compress_ws_kernel in tuning variant `variant`."""
+    kind "v1" = compress_kernel, anything else = compress_ws_kernel in tuning variant `variant`.
+    "v1" and variants > 0 only exist in -DNDZB_TUNING builds of the library (NDZB_EXTRA_NVCC_FLAGS=-DNDZB_TUNING);
+    with the default build those parametrisations are skipped."""
+    if kind == "v1" or (variant or 0) > 0:
+        import pytest
+        if not tuning_build():
+            pytest.skip("needs a -DNDZB_TUNING build of libndzip_b200.so")
     saved = {k: os.environ.get(k) for k in ("NDZB_COMPRESS_KERNEL", "NDZB_WS_VARIANT")}
     for k, v in (("NDZB_COMPRESS_KERNEL", kind), ("NDZB_WS_VARIANT", None if variant is None else str(variant))):
         if v is None:
@@ -42,6 +48,11 @@ def compress_kernel(kind=None, variant=None):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+def tuning_build():
+    from ndzip_b200 import _lib
+    return b"tuning" in _lib.load().ndzb_version()
 
 
 def _torch_bits(dtype):
