@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libndzip_b200.so")
+# NDZB_LIB selects another build of the same library (A/B runs of experimental kernels, scripts/build_variant.py)
+LIB_PATH = os.environ.get("NDZB_LIB") or os.path.join(HERE, "libndzip_b200.so")
 
 F32, F64 = 0, 1
 

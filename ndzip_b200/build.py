@@ -6,7 +6,7 @@ import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CSRC = os.path.join(HERE, "csrc")
+CSRC = os.environ.get("NDZB_CSRC") or os.path.join(HERE, "csrc")  # NDZB_CSRC: build another revision of the sources (A/B runs)
 LIB = os.path.join(HERE, "libndzip_b200.so")
 SOURCES = ["ndzb_kernels.cu", "ndzb_capi.cu", "ndzip_adapter.cu"]
 HEADERS = ["ndzb_cube.cuh", "ndzb_ptx.cuh", "ndzb_kernels.cuh"]
@@ -59,22 +59,37 @@ def build_tool(force: bool = False) -> str:
     return TOOL
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library if missing or older than its sources. Returns the .so path."""
-    if not force and not _stale():
-        return LIB
+def build(force: bool = False, verbose: bool = False, out: str | None = None, extra_flags: list[str] | None = None) -> str:
+    """Compile the CUDA library if missing or older than its sources. Returns the .so path.
+    `out` / `extra_flags` build a variant elsewhere (tuning builds: extra_flags=["-DNDZB_TUNING"])."""
+    lib = out or LIB
+    if out is None and not force and not _stale():
+        return lib
+    from concurrent.futures import ThreadPoolExecutor
     srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(os.path.dirname(HERE), "include"), "-o", LIB, *srcs]
-    if os.environ.get("NDZB_EXTRA_NVCC_FLAGS"):  # tuning builds, e.g. -DNDZB_DESC_STRIDE=4
-        cmd[1:1] = os.environ["NDZB_EXTRA_NVCC_FLAGS"].split()
+    flags = list(extra_flags or [])
+    if os.environ.get("NDZB_EXTRA_NVCC_FLAGS"):  # tuning builds, e.g. -DNDZB_TUNING -DNDZB_DESC_STRIDE=4
+        flags += os.environ["NDZB_EXTRA_NVCC_FLAGS"].split()
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+        flags.append("-Xptxas=-v")
     # nvcc must use the system g++ (the CXX in this image's environment points at a wrapper without libgomp specs)
     env = dict(os.environ)
     env.pop("CXX", None)
     env.pop("CC", None)
-    subprocess.run(cmd, check=True, env=env)
-    return LIB
+    objdir = os.path.join(os.path.dirname(HERE), "build", "obj_" + os.path.basename(lib).replace(".so", ""))
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    inc = ["-I", os.path.join(os.path.dirname(HERE), "include")]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        subprocess.run([_nvcc(), *flags, *compile_flags, *inc, "-c", "-o", obj, src], check=True, env=env)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as pool:  # the three translation units compile side by side
+        objs = list(pool.map(compile_one, srcs))
+    subprocess.run([_nvcc(), *NVCC_FLAGS, "-o", lib, *objs], check=True, env=env)
+    return lib
 
 
 if __name__ == "__main__":

@@ -84,22 +84,52 @@ uint32_t header_words(int dtype, uint32_t num_cubes) {
 
 size_t word_bytes(int dtype) { return dtype == NDZB_F32 ? 4 : 8; }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), the SM count and the occupancy tables are per device: one
+// configuration per device, filled on the first context created there.
+constexpr int kMaxDevices = 64;
 std::mutex g_config_mutex;
-kernel_config g_config;
-bool g_configured = false;
+kernel_config g_config[kMaxDevices];
+bool g_configured[kMaxDevices] = {};
+
+// Makes the context's device current for the duration of an entry point (a context is bound to the device that was
+// current when it was created: its scratch, streams and kernel attributes live there).
+class device_guard {
+  public:
+    explicit device_guard(int device) {
+        if (cudaGetDevice(&_previous) != cudaSuccess) _previous = -1;
+        if (_previous != device && cudaSetDevice(device) == cudaSuccess) _switched = true;
+    }
+    ~device_guard() {
+        if (_switched && _previous >= 0) cudaSetDevice(_previous);
+    }
+    device_guard(const device_guard &) = delete;
+    device_guard &operator=(const device_guard &) = delete;
+
+  private:
+    int _previous = -1;
+    bool _switched = false;
+};
+
+bool verbose() {  // reference src/ndzip/common.hh:628-631
+    const char *env = getenv("NDZIP_VERBOSE");
+    return env && *env;
+}
 
 }  // namespace
 
 struct ndzb_ctx {
     int dtype = 0;
     int dims = 0;
+    int device = 0;                   // the device that was current at ndzb_ctx_create; every entry point runs there
     cudaStream_t stream = nullptr;
     uint32_t desc_capacity = 0;
     uint64_t *d_desc = nullptr;       // look-back descriptors
     unsigned long long *d_blocks[2] = {nullptr, nullptr};  // block-level look-back words (one per 32 cubes, capacity as d_desc); the two
                                                             // arrays alternate between launches, each launch zeroes the other one
     int blocks_cur = 0;
-    uint32_t *d_counters = nullptr;   // [0] ticket counter, [1] total compressed words of the last launch
+    uint32_t *d_counters = nullptr;   // [0] ticket counter, [1] / [2] total compressed words of the last launch (the two
+                                      // alternate, so that a chained launch never reads its base from the word it writes)
+    int total_cur = 0;                // which of [1] / [2] the LAST launch wrote
     uint32_t ticket_base = 0;
     uint32_t epoch = 1;
     int forced_path = -1;             // NDZB_LOAD_PATH=tma|vec16|scalar (profiling / tests)
@@ -167,7 +197,7 @@ load_path choose_path(const ndzb_ctx *ctx, const void *data, const grid_geom &g)
 // Enqueue the compression of cubes [hc_begin, hc_begin + count) (count > 0).
 int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g, uint32_t hc_begin, uint32_t count,
         void *out_cubes, uint32_t *out_offsets, uint32_t *pad_word, uint32_t *length_out, uint32_t length_add,
-        const uint32_t *base_words = nullptr) {
+        bool chained = false) {
     if (int rc = ensure_descriptors(ctx, count)) return rc;
     const load_path path = choose_path(ctx, d_data, g);
     CUtensorMap map{};
@@ -176,8 +206,8 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
         if (r != CUDA_SUCCESS) return driver_fail(r, "cuTensorMapEncodeTiled");
     }
     const bool ws = path == load_path::tma && ctx->use_ws;
-    const int per_sm = ws ? 1 : g_config.ctas_per_sm[ctx->dtype][ctx->dims - 1][static_cast<int>(path)];
-    const uint64_t resident = static_cast<uint64_t>(per_sm > 0 ? per_sm : 1) * g_config.num_sms;
+    const int per_sm = ws ? 1 : g_config[ctx->device].ctas_per_sm[ctx->dtype][ctx->dims - 1][static_cast<int>(path)];
+    const uint64_t resident = static_cast<uint64_t>(per_sm > 0 ? per_sm : 1) * g_config[ctx->device].num_sms;
     const uint32_t grid = static_cast<uint32_t>(count < resident ? count : resident);
 
     compress_launch a{};
@@ -188,8 +218,11 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
     a.out_cubes = out_cubes;
     a.out_offsets = out_offsets;
     a.pad_word = pad_word;
-    a.base_words = base_words;
-    a.total_words = ctx->d_counters + 1;
+    // a chained launch starts where the previous one ended: it reads that total from one scalar and writes its own
+    // to the other, so the read never races with the write of the launch's last cube
+    a.base_words = chained ? ctx->d_counters + 1 + ctx->total_cur : nullptr;
+    ctx->total_cur ^= 1;
+    a.total_words = ctx->d_counters + 1 + ctx->total_cur;
     a.length_out = length_out;
     a.length_add = length_add;
     a.desc = ctx->d_desc;
@@ -266,9 +299,9 @@ bool store_vectorisable(const ndzb_ctx *ctx, const void *data, const grid_geom &
 int enqueue_decompress_range(ndzb_ctx *ctx, const void *stream_cubes, const uint32_t *offsets, void *d_data,
         const grid_geom &g, uint32_t hc_begin, uint32_t count) {
     const bool vec = store_vectorisable(ctx, d_data, g);
-    int per_sm = g_config.dec_ctas_per_sm[ctx->dtype][ctx->dims - 1][vec ? 1 : 0];
+    int per_sm = g_config[ctx->device].dec_ctas_per_sm[ctx->dtype][ctx->dims - 1][vec ? 1 : 0];
     if (ctx->dec_ctas_cap > 0 && per_sm > ctx->dec_ctas_cap) per_sm = ctx->dec_ctas_cap;  // NDZB_DEC_CTAS (tuning)
-    const uint64_t resident = static_cast<uint64_t>(per_sm > 0 ? per_sm : 1) * g_config.num_sms;
+    const uint64_t resident = static_cast<uint64_t>(per_sm > 0 ? per_sm : 1) * g_config[ctx->device].num_sms;
     const uint32_t grid = static_cast<uint32_t>(count < resident ? count : resident);
     decompress_launch a{};
     a.stream_cubes = stream_cubes;
@@ -388,11 +421,11 @@ int pipelined_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uint32
         NDZB_CUDA(cudaEventRecord(ctx->ev_k0[c], ctx->stream));
         const uint32_t hb = row0 * plan.cubes_per_row, he = row1 * plan.cubes_per_row;
         if (int rc = enqueue_compress_range(ctx, ctx->d_in, g, hb, he - hb, cubes, offsets + hb, c == 0 ? pad : nullptr,
-                    c + 1 == plan.chunks ? ctx->d_length : nullptr, hdr, c ? ctx->d_counters + 1 : nullptr)) {
+                    c + 1 == plan.chunks ? ctx->d_length : nullptr, hdr, c != 0)) {
             return rc;
         }
         NDZB_CUDA(cudaEventRecord(ctx->ev_k1[c], ctx->stream));
-        NDZB_CUDA(cudaMemcpyAsync(ctx->h_totals + c, ctx->d_counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        NDZB_CUDA(cudaMemcpyAsync(ctx->h_totals + c, ctx->d_counters + 1 + ctx->total_cur, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         NDZB_CUDA(cudaEventRecord(ctx->ev_done[c], ctx->stream));
     }
     // drain: as soon as a chunk's total is known on the host, its cubes go back on the copy-out stream
@@ -469,18 +502,23 @@ extern "C" {
 int ndzb_ctx_create(ndzb_ctx **out_ctx, int dtype, int dims, uint32_t max_hypercubes, void *cuda_stream) {
     if (!out_ctx || !valid_profile(dtype, dims)) return NDZB_ERR_INVALID_ARGUMENT;
     *out_ctx = nullptr;
+    int device = 0;
     {
+        const cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice (is a CUDA device present?)");
+        if (device < 0 || device >= kMaxDevices) return NDZB_ERR_INVALID_ARGUMENT;
         std::lock_guard<std::mutex> lock(g_config_mutex);
-        if (!g_configured) {
-            const cudaError_t e = configure_kernels(g_config);
-            if (e != cudaSuccess) return cuda_fail(e, "configure_kernels (is a CUDA device present?)");
-            g_configured = true;
+        if (!g_configured[device]) {
+            const cudaError_t c = configure_kernels(g_config[device]);
+            if (c != cudaSuccess) return cuda_fail(c, "configure_kernels (is a CUDA device present?)");
+            g_configured[device] = true;
         }
     }
     ndzb_ctx *ctx = new (std::nothrow) ndzb_ctx;
     if (!ctx) return NDZB_ERR_ALLOC;
     ctx->dtype = dtype;
     ctx->dims = dims;
+    ctx->device = device;
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     if (const char *p = getenv("NDZB_LOAD_PATH")) {
         if (!strcmp(p, "tma")) ctx->forced_path = 0;
@@ -496,9 +534,9 @@ int ndzb_ctx_create(ndzb_ctx **out_ctx, int dtype, int dims, uint32_t max_hyperc
         ndzb_ctx_destroy(ctx);
         return rc;
     };
-    cudaError_t e = cudaMalloc(&ctx->d_counters, 2 * sizeof(uint32_t));
+    cudaError_t e = cudaMalloc(&ctx->d_counters, 4 * sizeof(uint32_t));
     if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc counters"));
-    e = cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint32_t), ctx->stream);
+    e = cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(uint32_t), ctx->stream);
     if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMemsetAsync counters"));
     if (const char *p = getenv("NDZB_WS_CHECK")) ctx->ws_check = atoi(p) != 0;
     if (const char *p = getenv("NDZB_WS_DEBUG")) ctx->ws_debug = tuning_build() ? static_cast<uint32_t>(atoi(p)) : 0u;
@@ -541,6 +579,7 @@ void ndzb_host_free(void *ptr) {
 
 void ndzb_ctx_destroy(ndzb_ctx *ctx) {
     if (!ctx) return;
+    const device_guard on_device(ctx->device);
     if (ctx->d_desc) cudaFree(ctx->d_desc);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     for (auto b : ctx->d_blocks) {
@@ -583,7 +622,7 @@ int ndzb_compress(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t *s
         }
     }
     if (bg.count > 0) {
-        const cudaError_t e = launch_pack_border(ctx->dtype, d_data, bg, d_stream, hdr, H ? ctx->d_counters + 1 : nullptr, ctx->stream);
+        const cudaError_t e = launch_pack_border(ctx->dtype, d_data, bg, d_stream, hdr, H ? ctx->d_counters + 1 + ctx->total_cur : nullptr, ctx->stream);
         if (e != cudaSuccess) return cuda_fail(e, "pack_border launch");
         ctx->last_launches += 1;
     }

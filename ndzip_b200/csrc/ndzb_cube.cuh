@@ -112,31 +112,6 @@ NDZB_HD int popc32(uint32_t v) {
 #endif
 }
 
-// number of leading zero bits (32 / 64 for v == 0)
-NDZB_HD int clz32(uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    return __clz(static_cast<int>(v));
-#else
-    return v ? __builtin_clz(v) : 32;
-#endif
-}
-NDZB_HD int clz64(uint64_t v) {
-#if defined(__CUDA_ARCH__)
-    return __clzll(static_cast<long long>(v));
-#else
-    return v ? __builtin_clzll(v) : 64;
-#endif
-}
-// true when the set bits of v form ONE run (or v == 0): filling the trailing zeros gives 2^k - 1
-NDZB_HD bool one_run_of_ones(uint32_t v) {
-    const uint32_t t = v | (v - 1u);
-    return (t & (t + 1u)) == 0u;
-}
-NDZB_HD bool one_run_of_ones(uint64_t v) {
-    const uint64_t t = v | (v - 1ull);
-    return (t & (t + 1ull)) == 0ull;
-}
-
 NDZB_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t sel) {
 #if defined(__CUDA_ARCH__)
     return __byte_perm(x, y, sel);
@@ -426,30 +401,42 @@ NDZB_HD uint64_t planes_of_run(const uint64_t *r, uint32_t *planes_hi, uint32_t 
 // ([heads][non-zero planes of chunk 0][chunk 1]...), in place over the dead input tile, and then
 // copied out linearly (coalesced). Plane i of a chunk is emitted exactly when bit B-1-i of the chunk
 // head is set (reference src/ndzip/cpu_codec.inl:514-538). `body` = word offset of the chunk's first
-// plane inside the cube (C + exclusive plane count). Three issue slots per plane (test, predicated
-// store, predicated increment) instead of a warp-per-chunk pass over all 4096 plane slots.
+// plane inside the cube (C + exclusive plane count): a per-thread chain of predicated stores instead of a
+// warp-per-chunk pass over all 4096 plane slots.
 
-// Fast path: the head's set bits form one run (leading zero planes, then non-zero planes down to an optional block
-// of trailing zero planes — what smooth floating-point data produces almost always): plane i then lands at slot
-// i - clz(head), so every store has a compile-time offset from one base register: ONE predicated STS per plane and
-// no dependent pointer chain. Heads with holes take the general path (test, predicated store, predicated increment).
+// On the device the chain is written in PTX: per plane ONE predicated STS and ONE predicated pointer bump that is a
+// multiply-add with an opaque constant, so it issues on the fma pipe (the alu pipe bounds the kernel; see
+// complement_negative). The compiler's own code for the C loop below is test + predicated store + predicated add +
+// predicated move: three issue slots per plane, two of them alu. (A closed-form slot for heads whose set bits form
+// one run was tried first: real heads are "sign plane + gap + low run" with a few holes on top in ~15 % of the
+// chunks, so nearly every warp ran both paths — profiles/README.md round 2.)
+#if defined(__CUDA_ARCH__)
+// stores the planes whose head bits are set at *ptr (a shared-space byte address), advancing it. The bit tests stay in
+// C so that ptxas extracts the predicates seven at a time (R2P); store and pointer bump are PTX.
+__device__ __forceinline__ void emit_planes(uint32_t head, uint32_t &ptr, const uint32_t *planes, int stride_words) {
+    const uint32_t neg_stride = static_cast<uint32_t>(-4 * stride_words);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if ((head >> (31 - i)) & 1u) {
+            asm volatile("st.shared.u32 [%0], %1;\n\tmad.lo.u32 %0, %2, %3, %0;" : "+r"(ptr) : "r"(planes[i]), "r"(kFmaPipeConsts[0]), "r"(neg_stride) : "memory");
+        }
+    }
+}
+#endif
 
 // float: image is an array of 32-bit words
 NDZB_HD void compact_planes(uint32_t *image, int chunk, uint32_t head, uint32_t body, const uint32_t *planes) {
     image[chunk] = head;
     uint32_t *out = image + body;
-    if (one_run_of_ones(head)) {
-        uint32_t *base = out - clz32(head);
+#if defined(__CUDA_ARCH__)
+    uint32_t ptr = static_cast<uint32_t>(__cvta_generic_to_shared(out));
+    emit_planes(head, ptr, planes, 1);
+#else
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if ((head >> (31 - i)) & 1u) base[i] = planes[i];
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if ((head >> (31 - i)) & 1u) *out++ = planes[i];
-        }
+    for (int i = 0; i < 32; ++i) {
+        if ((head >> (31 - i)) & 1u) *out++ = planes[i];
     }
+#endif
 }
 
 // double: image is an array of 64-bit words seen as 32-bit halves (little endian: word w = halves
@@ -459,32 +446,26 @@ NDZB_HD void compact_planes(uint32_t *image, int chunk, bool first, uint64_t hea
     const uint32_t head_hi = static_cast<uint32_t>(head >> 32), head_lo = static_cast<uint32_t>(head);
     image[2 * chunk + (first ? 1 : 0)] = first ? head_hi : head_lo;
     uint32_t *out = image + 2 * body + (first ? 1 : 0);
-    if (one_run_of_ones(head)) {
-        uint32_t *base = out - 2 * clz64(head);
+#if defined(__CUDA_ARCH__)
+    uint32_t ptr = static_cast<uint32_t>(__cvta_generic_to_shared(out));
+    emit_planes(head_hi, ptr, planes_hi, 2);
+    emit_planes(head_lo, ptr, planes_lo, 2);
+#else
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if ((head_hi >> (31 - i)) & 1u) base[2 * i] = planes_hi[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if ((head_lo >> (31 - i)) & 1u) base[64 + 2 * i] = planes_lo[i];
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if ((head_hi >> (31 - i)) & 1u) {
-                *out = planes_hi[i];
-                out += 2;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if ((head_lo >> (31 - i)) & 1u) {
-                *out = planes_lo[i];
-                out += 2;
-            }
+    for (int i = 0; i < 32; ++i) {
+        if ((head_hi >> (31 - i)) & 1u) {
+            *out = planes_hi[i];
+            out += 2;
         }
     }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if ((head_lo >> (31 - i)) & 1u) {
+            *out = planes_lo[i];
+            out += 2;
+        }
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -492,25 +473,36 @@ NDZB_HD void compact_planes(uint32_t *image, int chunk, bool first, uint64_t hea
 // transpose is an involution, reference src/test/codec_generic_test.cc:65-81), complement undone
 // (common.hh:505-507)
 
+#if defined(__CUDA_ARCH__)
+// a[31 - i] = plane i of the chunk: loaded from *ptr (shared-space byte address, advanced) when the head bit is set,
+// 0 otherwise. Same shape as emit_planes: one predicated LDS and one predicated fma-pipe pointer bump per plane.
+__device__ __forceinline__ void fetch_planes(uint32_t head, uint32_t &ptr, uint32_t *a, int stride_words) {
+    const uint32_t neg_stride = static_cast<uint32_t>(-4 * stride_words);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        uint32_t v = 0;
+        if ((head >> (31 - i)) & 1u) {
+            asm volatile("ld.shared.u32 %1, [%0];\n\tmad.lo.u32 %0, %2, %3, %0;" : "+r"(ptr), "=r"(v) : "r"(kFmaPipeConsts[0]), "r"(neg_stride) : "memory");
+        }
+        a[31 - i] = v;
+    }
+}
+#endif
+
 NDZB_HD void run_of_image(const uint32_t *image, uint32_t head, uint32_t body, uint32_t *r) {
     uint32_t a[32];
     const uint32_t *in = image + body;
-    if (one_run_of_ones(head)) {  // see compact_planes: plane i sits at slot i - clz(head); independent loads
-        const uint32_t *base = in - clz32(head);
+#if defined(__CUDA_ARCH__)
+    uint32_t ptr = static_cast<uint32_t>(__cvta_generic_to_shared(in));
+    fetch_planes(head, ptr, a, 1);
+#else
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            uint32_t v = 0;
-            if ((head >> (31 - i)) & 1u) v = base[i];
-            a[31 - i] = v;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            uint32_t v = 0;
-            if ((head >> (31 - i)) & 1u) v = *in++;
-            a[31 - i] = v;
-        }
+    for (int i = 0; i < 32; ++i) {
+        uint32_t v = 0;
+        if ((head >> (31 - i)) & 1u) v = *in++;
+        a[31 - i] = v;
     }
+#endif
     transpose32(a);
 #pragma unroll
     for (int j = 0; j < 32; ++j) r[j] = complement_negative(a[31 - j]);
@@ -520,40 +512,30 @@ NDZB_HD void run_of_image(const uint32_t *image, bool first, uint64_t head, uint
     const uint32_t head_hi = static_cast<uint32_t>(head >> 32), head_lo = static_cast<uint32_t>(head);
     uint32_t a[32], b[32];
     const uint32_t *in = image + 2 * body + (first ? 1 : 0);
-    if (one_run_of_ones(head)) {
-        const uint32_t *base = in - 2 * clz64(head);
+#if defined(__CUDA_ARCH__)
+    uint32_t ptr = static_cast<uint32_t>(__cvta_generic_to_shared(in));
+    fetch_planes(head_hi, ptr, a, 2);
+    fetch_planes(head_lo, ptr, b, 2);
+#else
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            uint32_t v = 0;
-            if ((head_hi >> (31 - i)) & 1u) v = base[2 * i];
-            a[31 - i] = v;
+    for (int i = 0; i < 32; ++i) {
+        uint32_t v = 0;
+        if ((head_hi >> (31 - i)) & 1u) {
+            v = *in;
+            in += 2;
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            uint32_t v = 0;
-            if ((head_lo >> (31 - i)) & 1u) v = base[64 + 2 * i];
-            b[31 - i] = v;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            uint32_t v = 0;
-            if ((head_hi >> (31 - i)) & 1u) {
-                v = *in;
-                in += 2;
-            }
-            a[31 - i] = v;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            uint32_t v = 0;
-            if ((head_lo >> (31 - i)) & 1u) {
-                v = *in;
-                in += 2;
-            }
-            b[31 - i] = v;
-        }
+        a[31 - i] = v;
     }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        uint32_t v = 0;
+        if ((head_lo >> (31 - i)) & 1u) {
+            v = *in;
+            in += 2;
+        }
+        b[31 - i] = v;
+    }
+#endif
     transpose32(a);
     transpose32(b);
 #pragma unroll

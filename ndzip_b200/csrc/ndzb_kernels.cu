@@ -320,6 +320,11 @@ __device__ __forceinline__ void issue_tma_load(
         ptx::tma_load_2d(slot, map, bar, 0, cx * 128);
     } else if constexpr (sizeof(Bits) == 4 && Dims == 2) {
         ptx::tma_load_3d(slot, map, bar, 0, cx * 2, cy * 64);
+    } else if constexpr (sizeof(Bits) == 4 && Dims == 3) {
+        // ONE copy for both y-parity regions: the view's slowest dimension is the parity (make_input_tensor_map), so the
+        // box [par][z][y/2][x] lands as region 0 = even rows, region 1 = odd rows. Two copies of 128 rows of 64 bytes each
+        // reach 4.9 TB/s, this one 6.0 TB/s (scripts/ubench/tma_shapes.cu, profiles/README.md round 2).
+        ptx::tma_load_4d(slot, map, bar, cx * 16, cy * 8, cz * 16, 0);
     } else {
         // two regions: float 3D = even-y / odd-y rows (view [z][y/2][y parity][x], SWIZZLE_64B);
         //              double   = first / second 16-value half of every run
@@ -879,7 +884,6 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                 }
                 const uint32_t t = tk[j];
                 if (t < a.count) {
-                    if constexpr (LA > 0) tk[j] = atomicAdd(a.ticket, 1u) - a.ticket_base;
                     aux.ticket[s] = t;
                     aux.seq[s] = seq;
                     if (Stats) {
@@ -887,8 +891,14 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                         if (!first_round) st_c += static_cast<uint32_t>(c - aux.freed[s]);  // freed -> TMA issued
                         aux.issued[s] = c;
                     }
+#if defined(NDZB_LOADER_FENCE)
                     ptx::fence_proxy_async_smem();  // the slot's previous life (generic reads/writes) before the TMA write
+#endif
                     issue_tma_load<Bits, Dims>(slots + s * slot_words, &aux.full[s], &in_map, a.geom, a.hc_begin + t);
+                    // The next ticket is drawn AFTER the load is on its way: the proxy fence above is a MEMBAR, which
+                    // waits for every memory operation this thread has in flight — with the atomic in front of it the
+                    // loader stood still for an L2 round trip per cube (slot free -> load issued: 2300 cycles).
+                    if constexpr (LA > 0) tk[j] = atomicAdd(a.ticket, 1u) - a.ticket_base;
                 } else {
                     aux.ticket[s] = kNoTicket - poison;  // end marker number `poison`
                     aux.seq[s] = seq;
@@ -978,7 +988,9 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                 constexpr uint32_t w32 = sizeof(Bits) / 4;
                 copy_image_out(slots + s * slot_words, reinterpret_cast<uint32_t *>(out_cubes + exclusive), words * w32, lane);
             }
+#if !defined(NDZB_NO_RETIRE_FENCE)
             ptx::fence_proxy_async_smem();   // these generic reads before the next TMA load into the slot
+#endif
             __syncwarp();
             if (Stats && lane == 0) aux.freed[s] = static_cast<uint32_t>(clock64());
             if (lane == 0) ptx::mbar_arrive(&aux.empty[s]);
@@ -1262,11 +1274,12 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
             __syncthreads();
             S carry{{0, 0}};
             for (int sg = 0; sg < seg; ++sg) carry = carry + S{{aux.segment_total[sg][2 * xq], aux.segment_total[sg][2 * xq + 1]}};
-            Bits *dst = data + origin + static_cast<uint64_t>(seg * 16) * a.geom.n[2] + xq * 2;
+            char *dst = reinterpret_cast<char *>(data + origin + static_cast<uint64_t>(seg * 16) * a.geom.n[2] + xq * 2);
+            const uint64_t row_bytes = static_cast<uint64_t>(a.geom.n[2]) * sizeof(Bits);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                (q[k] + carry).template emit<Vec16>(dst);
-                dst += a.geom.n[2];
+                (q[k] + carry).template emit<Vec16>(reinterpret_cast<Bits *>(dst));
+                dst += row_bytes;
             }
         } else {
             // ---- y direction in the tile, z direction fused with rotate + store; 16 x 8 strips per pass -
@@ -1290,14 +1303,16 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
                 S q[16];
 #pragma unroll
                 for (int z = 0; z < 16; ++z) q[z] = S::load(tile + col.at(z));
-                const uint64_t plane = static_cast<uint64_t>(a.geom.n[1]) * a.geom.n[2];
-                Bits *dst = data + origin + static_cast<uint64_t>(o) * a.geom.n[2] + xq * 2;
-                q[0].template emit<Vec16>(dst);
+                // one byte pointer advanced by the plane pitch (a 64-bit add per store) instead of an element index
+                // that is multiplied out and scaled for every store (IMAD.WIDE + LEA + LEA.HI.X)
+                const uint64_t plane_bytes = static_cast<uint64_t>(a.geom.n[1]) * a.geom.n[2] * sizeof(Bits);
+                char *dst = reinterpret_cast<char *>(data + origin + static_cast<uint64_t>(o) * a.geom.n[2] + xq * 2);
+                q[0].template emit<Vec16>(reinterpret_cast<Bits *>(dst));
 #pragma unroll
                 for (int z = 1; z < 16; ++z) {
                     q[z] = q[z] + q[z - 1];
-                    dst += plane;
-                    q[z].template emit<Vec16>(dst);
+                    dst += plane_bytes;
+                    q[z].template emit<Vec16>(reinterpret_cast<Bits *>(dst));
                 }
             }
         }
@@ -1401,13 +1416,18 @@ struct ws_variant {
 // B200 with descriptors one per 64 bytes (profiles/README.md): float 5 groups + 4 retire warps + two-level look-back
 // (3-D 0.193 ms, 1-D 0.297 ms per GiB), double 3 + 2 with 32-cube windows (2-D 0.199 ms).
 #if defined(NDZB_TUNING)
-constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}, {5, 3, 2, 1, 0, 0, false, false}, {5, 4, 1, 1, 0, 1, true, false},
-        {4, 4, -2, 0, 0, 1, false, false}, {5, 4, 0, 1, 3, 1, false, true}};
-constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 2, 2, 1, 0, 0, false, false}, {3, 2, 0, 1, 0, 1, true, false},
-        {3, 3, -2, 0, 0, 1, false, false}, {3, 2, 1, 1, 2, 1, false, true}};
+constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}, {5, 4, 0, 0, 0, 1, false, false}, {5, 4, 0, 0, 0, 1, true, false},
+        {5, 4, 0, 1, 0, 1, true, false}, {5, 4, 0, 1, 0, 1, false, true}, {5, 5, 0, 1, 0, 1, false, false}, {5, 6, 0, 1, 0, 1, false, false},
+        {5, 5, 0, 0, 0, 1, true, false}};
+constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 2, 1, 0, 0, 1, false, false}, {3, 2, 1, 0, 0, 1, true, false},
+        {3, 2, 1, 1, 0, 1, true, false}, {3, 2, 1, 1, 0, 1, false, true}, {3, 3, 1, 1, 0, 1, false, false}, {3, 4, 1, 1, 0, 1, false, false},
+        {3, 3, 0, 1, 0, 1, false, false}};
 #else
-constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}};
-constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}};
+#ifndef NDZB_LA
+#define NDZB_LA 1
+#endif
+constexpr ws_variant kWsVariants32[] = {{5, 4, 0, NDZB_LA, 0, 1, false, false}};
+constexpr ws_variant kWsVariants64[] = {{3, 2, 1, NDZB_LA, 0, 1, false, false}};
 #endif
 constexpr int kNumWsVariants32 = sizeof(kWsVariants32) / sizeof(ws_variant);
 constexpr int kNumWsVariants64 = sizeof(kWsVariants64) / sizeof(ws_variant);
@@ -1433,6 +1453,9 @@ compress_ws_fn compress_ws_for(int variant) {
         case 2: return compress_ws_variant_fn<Bits, Dims, 2>();
         case 3: return compress_ws_variant_fn<Bits, Dims, 3>();
         case 4: return compress_ws_variant_fn<Bits, Dims, 4>();
+        case 5: return compress_ws_variant_fn<Bits, Dims, 5>();
+        case 6: return compress_ws_variant_fn<Bits, Dims, 6>();
+        case 7: return compress_ws_variant_fn<Bits, Dims, 7>();
         default: break;
     }
 #endif
@@ -1630,11 +1653,11 @@ CUresult make_input_tensor_map(CUtensorMap *map, int dtype, int dims, const void
             gdim[0] = 32; gdim[1] = n2 / 32; gdim[2] = n1;
             gstride[0] = 128; gstride[1] = n2 * 4;
             box[0] = 32; box[1] = 2; box[2] = 64;
-        } else {                    // [z][y / 2][y parity][x]; 64-byte inner rows -> SWIZZLE_64B
+        } else {                    // [y parity][z][y / 2][x] (strides need not be monotonic); 64-byte inner rows -> SWIZZLE_64B
             rank = 4;
-            gdim[0] = n2; gdim[1] = 2; gdim[2] = n1 / 2; gdim[3] = n0;
-            gstride[0] = n2 * 4; gstride[1] = n2 * 8; gstride[2] = n1 * n2 * 4;
-            box[0] = 16; box[1] = 1; box[2] = 8; box[3] = 16;
+            gdim[0] = n2; gdim[1] = n1 / 2; gdim[2] = n0; gdim[3] = 2;
+            gstride[0] = n2 * 8; gstride[1] = n1 * n2 * 4; gstride[2] = n2 * 4;
+            box[0] = 16; box[1] = 8; box[2] = 16; box[3] = 2;
             swizzle = CU_TENSOR_MAP_SWIZZLE_64B;
         }
     } else {
