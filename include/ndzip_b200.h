@@ -36,7 +36,9 @@ typedef enum ndzb_status {
     NDZB_ERR_DIMS_MISMATCH = -2,    /* reference: std::runtime_error, src/ndzip/cuda_codec.inl:557-559, 631-633 */
     NDZB_ERR_CAPACITY = -3,         /* more hypercubes than the context was created for (compressor_requirements) */
     NDZB_ERR_CUDA = -4,             /* a CUDA runtime/driver call failed; see ndzb_last_cuda_error() */
-    NDZB_ERR_ALLOC = -5
+    NDZB_ERR_ALLOC = -5,
+    NDZB_ERR_CORRUPT_STREAM = -6    /* host-pointer decompression: the header is not monotonic, a cube exceeds its bound, or
+                                       the stream ends before header + cubes + border (nothing was enqueued) */
 } ndzb_status;
 
 /* Opaque per-stream context. Owns the scratch the reference's cuda_compressor_impl owns
@@ -67,7 +69,10 @@ int ndzb_decompress(ndzb_ctx *ctx, const void *d_stream, void *d_data, int dims,
  * byte sizes are 64-bit (the reference re-allocates per call and overflows at 4 GiB,
  * cuda_codec.inl:679-685). `kernel_ns` (nullable) receives the cudaEvent interval around the kernels
  * only, the reference's kernel_duration (cuda_codec.inl:687-704).
- * ndzb_offload_decompress returns in `consumed_words` the stream words consumed (offload.hh:21-24). */
+ * ndzb_offload_decompress returns in `consumed_words` the stream words consumed (offload.hh:21-24). It validates the
+ * header on the host first (offsets non-decreasing, every cube within ndzb_compressed_cube_bound, header + cubes +
+ * border inside `length_words`) and fails with NDZB_ERR_CORRUPT_STREAM before touching the device otherwise; only the
+ * words the stream occupies are uploaded. */
 int ndzb_offload_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uint32_t *size, void *h_stream,
         uint32_t *length_words, uint64_t *kernel_ns);
 int ndzb_offload_decompress(ndzb_ctx *ctx, const void *h_stream, uint32_t length_words, void *h_data, int dims,
@@ -101,6 +106,70 @@ int ndzb_pack_border(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t
 /* Decompresses the hypercube range [hc_begin, hc_end) of a complete stream into d_data (global base). */
 int ndzb_decompress_cubes(ndzb_ctx *ctx, const void *d_stream, void *d_data, int dims, const uint32_t *size,
         uint32_t hc_begin, uint32_t hc_end);
+
+/* Same kernel as ndzb_fixup_header on an explicit stream, without a context (used by the multi-GPU data plane, whose
+ * exchange runs on a side stream). */
+int ndzb_fixup_header_on(void *cuda_stream, const uint32_t *d_local_header, uint32_t *d_global_header, uint32_t count,
+        const uint32_t *d_gathered_lengths, const uint32_t *d_overhead_words, uint32_t rank);
+
+/* ---- Multi-GPU data plane (new work; BASELINE.json configs[3], configs[4]) ---------------------
+ * The grid is cut into slabs of whole cube rows along dimension 0, one per rank (one process per GPU, or one host
+ * thread per GPU in a single process). Every rank compresses its slab into a SELF-CONTAINED ndzip stream of the slab
+ * (the reference decoder reads it with the slab's extent). The data path has one exchange step — an ncclAllGather of
+ * one uint32 per rank (the stream lengths) on a high-priority side stream, then one kernel that rewrites the rank's
+ * "offset_after" header entries (reference src/ndzip/common.hh:342-358) for the global stream — and an optional
+ * final gather (ncclSend / ncclRecv straight into place on the root), after which the root holds the stream the
+ * reference produces for the whole grid, bit for bit. NCCL is bound with dlopen("libnccl.so.2") on first use. */
+typedef struct ndzb_dist ndzb_dist;
+#define NDZB_UNIQUE_ID_BYTES 128
+
+/* Where a rank's pieces live (all counts in stream words of the dtype unless noted). Pure geometry: no GPU needed. */
+typedef struct ndzb_dist_layout {
+    uint32_t slab_begin, slab_end;   /* [begin, end) along dimension 0 of the global grid */
+    uint32_t slab_size[3];           /* extent of the slab (dims entries) */
+    uint32_t local_cubes;            /* hypercubes of the slab */
+    uint32_t cube_index_base;        /* global index of the slab's first hypercube */
+    uint32_t local_header_words;
+    uint64_t local_border_words;     /* border elements of the slab = words */
+    uint64_t border_base;            /* border words of the lower ranks */
+    uint64_t local_bound_words;      /* ndzb_compressed_length_bound of the slab: size of the local stream buffer */
+    uint32_t global_cubes;
+    uint32_t global_header_words;
+    uint64_t global_border_words;
+    uint64_t global_bound_words;     /* size of the root's buffer for ndzb_dist_gather */
+} ndzb_dist_layout;
+int ndzb_dist_plan(int dtype, int dims, const uint32_t *global_size, int world, int rank, ndzb_dist_layout *out);
+
+/* Bootstrap. Multi-process: rank 0 calls ndzb_dist_unique_id and ships the 128 bytes to the other ranks by any means
+ * (torch.distributed broadcast, MPI, a file); every rank then calls ndzb_dist_create on its own device (collective:
+ * ncclCommInitRank). Single process: ndzb_dist_create_local fills out[0..world) for `devices` (ncclCommInitAll,
+ * one non-blocking stream per rank); afterwards each rank must be driven by its own host thread.
+ * world == 1 needs no NCCL. The object owns an ndzb_ctx for the slab. */
+int ndzb_dist_unique_id(void *id128);
+int ndzb_dist_create(ndzb_dist **out, int dtype, int dims, const uint32_t *global_size, const void *id128, int rank, int world,
+        void *cuda_stream);
+int ndzb_dist_create_local(ndzb_dist **out, int dtype, int dims, const uint32_t *global_size, int world, const int *devices);
+void ndzb_dist_destroy(ndzb_dist *d);
+int ndzb_dist_layout_of(const ndzb_dist *d, int rank, ndzb_dist_layout *out);
+void *ndzb_dist_stream(const ndzb_dist *d); /* the cudaStream_t everything below is enqueued on */
+
+/* Compresses the rank's slab (d_slab = its first element) into d_local_stream (layout.local_bound_words words) on the
+ * object's stream and starts the exchange on the side stream. d_local_length (nullable, device) receives the local
+ * stream length. Asynchronous; nothing after it on the object's stream waits for the exchange. */
+int ndzb_dist_compress(ndzb_dist *d, const void *d_slab, void *d_local_stream, uint32_t *d_local_length);
+/* Decompresses the slab from its local stream (no communication). */
+int ndzb_dist_decompress(ndzb_dist *d, const void *d_local_stream, void *d_slab);
+/* Makes the object's stream wait for the exchange of the last ndzb_dist_compress; afterwards the two arrays below are
+ * valid there: the rank's slice of the GLOBAL header (local_cubes uint32 entries) and every rank's stream length. */
+int ndzb_dist_wait_exchange(ndzb_dist *d);
+const uint32_t *ndzb_dist_global_header(const ndzb_dist *d);
+const uint32_t *ndzb_dist_gathered_lengths(const ndzb_dist *d);
+/* Final stream gather (collective). d_global_stream (root only, layout.global_bound_words words) receives the whole
+ * grid's stream; *global_length_words (nullable, host, every rank) its length. Synchronises the object's stream once
+ * (the send / receive sizes must be known on the host), then enqueues the transfers and returns. */
+int ndzb_dist_gather(ndzb_dist *d, const void *d_local_stream, void *d_global_stream, int root, uint64_t *global_length_words);
+/* NCCL / CUDA error text of the last failing ndzb_dist_* call on this thread. */
+const char *ndzb_dist_last_error(void);
 
 /* Host-side stream arithmetic (no GPU needed). */
 /* src/ndzip/common.hh:395-412 */

@@ -37,7 +37,33 @@ SYMBOLS = [
     ("ndzb_last_cuda_error", ctypes.c_char_p, []),
     ("ndzb_version", ctypes.c_char_p, []),
     ("ndzb_last_launch_count", _u32, [_vp]),
+    ("ndzb_fixup_header_on", _i, [_vp, _vp, _vp, _u32, _vp, _vp, _u32]),
+    # multi-GPU data plane
+    ("ndzb_dist_plan", _i, [_i, _i, _vp, _i, _i, _vp]),
+    ("ndzb_dist_unique_id", _i, [_vp]),
+    ("ndzb_dist_create", _i, [ctypes.POINTER(_vp), _i, _i, _vp, _vp, _i, _i, _vp]),
+    ("ndzb_dist_create_local", _i, [ctypes.POINTER(_vp), _i, _i, _vp, _i, _vp]),
+    ("ndzb_dist_destroy", None, [_vp]),
+    ("ndzb_dist_layout_of", _i, [_vp, _i, _vp]),
+    ("ndzb_dist_stream", _vp, [_vp]),
+    ("ndzb_dist_compress", _i, [_vp, _vp, _vp, _vp]),
+    ("ndzb_dist_decompress", _i, [_vp, _vp, _vp]),
+    ("ndzb_dist_wait_exchange", _i, [_vp]),
+    ("ndzb_dist_global_header", _vp, [_vp]),
+    ("ndzb_dist_gathered_lengths", _vp, [_vp]),
+    ("ndzb_dist_gather", _i, [_vp, _vp, _vp, _i, _pu64]),
+    ("ndzb_dist_last_error", ctypes.c_char_p, []),
 ]
+
+
+class DistLayout(ctypes.Structure):
+    """struct ndzb_dist_layout (include/ndzip_b200.h)"""
+    _fields_ = [
+        ("slab_begin", _u32), ("slab_end", _u32), ("slab_size", _u32 * 3), ("local_cubes", _u32),
+        ("cube_index_base", _u32), ("local_header_words", _u32), ("local_border_words", _u64), ("border_base", _u64),
+        ("local_bound_words", _u64), ("global_cubes", _u32), ("global_header_words", _u32),
+        ("global_border_words", _u64), ("global_bound_words", _u64),
+    ]
 
 _lib = None
 
@@ -67,7 +93,9 @@ def check(status: int) -> None:
         lib = load()
         msg = lib.ndzb_strerror(status).decode()
         if status == -4:
-            msg += ": " + lib.ndzb_last_cuda_error().decode()
+            detail = lib.ndzb_last_cuda_error().decode()
+            dist_detail = lib.ndzb_dist_last_error().decode()
+            msg += ": " + (dist_detail if dist_detail != "no error" and detail == "no error" else detail)
         raise NdzipB200Error(msg)
 
 

@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.environ.get("NDZB_CSRC") or os.path.join(HERE, "csrc")  # NDZB_CSRC: build another revision of the sources (A/B runs)
 LIB = os.path.join(HERE, "libndzip_b200.so")
-SOURCES = ["ndzb_kernels.cu", "ndzb_capi.cu", "ndzip_adapter.cu"]
+SOURCES = ["ndzb_kernels.cu", "ndzb_capi.cu", "ndzb_dist.cu", "ndzip_adapter.cu"]
 HEADERS = ["ndzb_cube.cuh", "ndzb_ptx.cuh", "ndzb_kernels.cuh"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -88,7 +88,7 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None, ex
 
     with ThreadPoolExecutor(max_workers=len(srcs)) as pool:  # the three translation units compile side by side
         objs = list(pool.map(compile_one, srcs))
-    subprocess.run([_nvcc(), *NVCC_FLAGS, "-o", lib, *objs], check=True, env=env)
+    subprocess.run([_nvcc(), *NVCC_FLAGS, "-o", lib, *objs, "-ldl"], check=True, env=env)
     return lib
 
 

@@ -114,6 +114,10 @@ bool verbose() {  // reference src/ndzip/common.hh:628-631
     const char *env = getenv("NDZIP_VERBOSE");
     return env && *env;
 }
+// what the reference's offloader prints under NDZIP_VERBOSE (src/ndzip/cuda_codec.inl:699-703, 746-748)
+void report_kernel_time(uint64_t ns) {
+    if (verbose()) printf("[profile] total kernel time %.3fms\n", static_cast<double>(ns) * 1e-6);
+}
 
 }  // namespace
 
@@ -604,6 +608,7 @@ void ndzb_ctx_destroy(ndzb_ctx *ctx) {
 int ndzb_compress(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t *size, void *d_stream,
         uint32_t *d_length_words) {
     if (int rc = check_call(ctx, dims, size)) return rc;
+    const device_guard on_device(ctx->device);
     ctx->last_launches = 0;
     const grid_geom g = make_geom(dims, size);
     const border_geom bg = make_border(dims, size);
@@ -636,6 +641,7 @@ int ndzb_compress(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t *s
 
 int ndzb_decompress(ndzb_ctx *ctx, const void *d_stream, void *d_data, int dims, const uint32_t *size) {
     if (int rc = check_call(ctx, dims, size)) return rc;
+    const device_guard on_device(ctx->device);
     ctx->last_launches = 0;
     const grid_geom g = make_geom(dims, size);
     const border_geom bg = make_border(dims, size);
@@ -658,6 +664,7 @@ int ndzb_decompress(ndzb_ctx *ctx, const void *d_stream, void *d_data, int dims,
 int ndzb_compress_cubes(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t *size, uint32_t hc_begin,
         uint32_t hc_end, void *d_cubes, uint32_t *d_offsets_after, uint32_t *d_local_words) {
     if (int rc = check_call(ctx, dims, size)) return rc;
+    const device_guard on_device(ctx->device);
     ctx->last_launches = 0;
     const grid_geom g = make_geom(dims, size);
     if (hc_begin > hc_end || hc_end > g.num_cubes || !d_local_words) return NDZB_ERR_INVALID_ARGUMENT;
@@ -673,6 +680,7 @@ int ndzb_compress_cubes(ndzb_ctx *ctx, const void *d_data, int dims, const uint3
 
 int ndzb_add_offset(ndzb_ctx *ctx, uint32_t *d_offsets, uint32_t count, const uint32_t *d_base_words) {
     if (!ctx || (count && (!d_offsets || !d_base_words))) return NDZB_ERR_INVALID_ARGUMENT;
+    const device_guard on_device(ctx->device);
     const cudaError_t e = launch_add_offset(d_offsets, count, d_base_words, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(e, "add_offset launch");
     return NDZB_OK;
@@ -683,13 +691,26 @@ int ndzb_fixup_header(ndzb_ctx *ctx, const uint32_t *d_local_header, uint32_t *d
     if (!ctx || (count && (!d_local_header || !d_global_header)) || (rank && (!d_gathered_lengths || !d_overhead_words))) {
         return NDZB_ERR_INVALID_ARGUMENT;
     }
+    const device_guard on_device(ctx->device);
     const cudaError_t e = launch_fixup_header(d_local_header, d_global_header, count, d_gathered_lengths, d_overhead_words, rank, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "fixup_header launch");
+    return NDZB_OK;
+}
+
+int ndzb_fixup_header_on(void *cuda_stream, const uint32_t *d_local_header, uint32_t *d_global_header, uint32_t count,
+        const uint32_t *d_gathered_lengths, const uint32_t *d_overhead_words, uint32_t rank) {
+    if ((count && (!d_local_header || !d_global_header)) || (rank && (!d_gathered_lengths || !d_overhead_words))) {
+        return NDZB_ERR_INVALID_ARGUMENT;
+    }
+    const cudaError_t e = launch_fixup_header(d_local_header, d_global_header, count, d_gathered_lengths, d_overhead_words, rank,
+            static_cast<cudaStream_t>(cuda_stream));
     if (e != cudaSuccess) return cuda_fail(e, "fixup_header launch");
     return NDZB_OK;
 }
 
 int ndzb_pack_border(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t *size, void *d_out) {
     if (int rc = check_call(ctx, dims, size)) return rc;
+    const device_guard on_device(ctx->device);
     const border_geom bg = make_border(dims, size);
     if (bg.count == 0) return NDZB_OK;
     if (!d_data || !d_out) return NDZB_ERR_INVALID_ARGUMENT;
@@ -701,6 +722,7 @@ int ndzb_pack_border(ndzb_ctx *ctx, const void *d_data, int dims, const uint32_t
 int ndzb_decompress_cubes(ndzb_ctx *ctx, const void *d_stream, void *d_data, int dims, const uint32_t *size,
         uint32_t hc_begin, uint32_t hc_end) {
     if (int rc = check_call(ctx, dims, size)) return rc;
+    const device_guard on_device(ctx->device);
     ctx->last_launches = 0;
     const grid_geom g = make_geom(dims, size);
     if (hc_begin > hc_end || hc_end > g.num_cubes) return NDZB_ERR_INVALID_ARGUMENT;
@@ -719,6 +741,8 @@ int ndzb_offload_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uin
     const size_t in_bytes = num_elements(dims, size) * wb;                                        // 64-bit, cf. cuda_codec.inl:681
     const size_t bound_bytes = ndzb_compressed_length_bound(ctx->dtype, dims, size) * wb;
     if (in_bytes && (!h_data || !h_stream)) return NDZB_ERR_INVALID_ARGUMENT;
+    const device_guard on_device(ctx->device);
+    if (verbose()) printf("Have %u hypercubes\n", ndzb_num_hypercubes(dims, size));  // cuda_codec.inl:676-678
     if (int rc = ensure_buffer(&ctx->d_in, &ctx->d_in_bytes, in_bytes ? in_bytes : 16)) return rc;
     if (int rc = ensure_buffer(&ctx->d_out, &ctx->d_out_bytes, bound_bytes ? bound_bytes : 16)) return rc;
     if (!ctx->d_length) NDZB_CUDA(cudaMalloc(&ctx->d_length, sizeof(uint32_t)));
@@ -728,8 +752,11 @@ int ndzb_offload_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uin
             const chunk_plan plan = plan_chunks(dims, size, g, wb);
             if (plan.chunks > 1) {
                 ctx->last_launches = 0;
-                const int rc = pipelined_compress(ctx, h_data, dims, size, h_stream, length_words, kernel_ns, g, plan);
+                uint64_t ns = 0;
+                const int rc = pipelined_compress(ctx, h_data, dims, size, h_stream, length_words, (kernel_ns || verbose()) ? &ns : nullptr, g, plan);
                 ctx->last_launches = static_cast<uint32_t>(plan.chunks);
+                if (kernel_ns) *kernel_ns = ns;
+                if (rc == NDZB_OK) report_kernel_time(ns);
                 return rc;
             }
         }
@@ -743,10 +770,12 @@ int ndzb_offload_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uin
     NDZB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (len) NDZB_CUDA(cudaMemcpyAsync(h_stream, ctx->d_out, static_cast<size_t>(len) * wb, cudaMemcpyDeviceToHost, ctx->stream));
     NDZB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (kernel_ns) {
+    if (kernel_ns || verbose()) {
         float ms = 0;
         NDZB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
-        *kernel_ns = static_cast<uint64_t>(static_cast<double>(ms) * 1e6);
+        const uint64_t ns = static_cast<uint64_t>(static_cast<double>(ms) * 1e6);
+        if (kernel_ns) *kernel_ns = ns;
+        report_kernel_time(ns);
     }
     *length_words = len;
     return NDZB_OK;
@@ -757,8 +786,30 @@ int ndzb_offload_decompress(ndzb_ctx *ctx, const void *h_stream, uint32_t length
     if (int rc = check_call(ctx, dims, size)) return rc;
     const size_t wb = word_bytes(ctx->dtype);
     const size_t out_bytes = num_elements(dims, size) * wb;
-    const size_t in_bytes = static_cast<size_t>(length_words) * wb;
     if (out_bytes && (!h_data || !h_stream)) return NDZB_ERR_INVALID_ARGUMENT;
+    const device_guard on_device(ctx->device);
+    // The header is in host memory: check it before anything is enqueued. A truncated or corrupt stream (the tool hands
+    // over whatever is left of a file) must not turn into out-of-bounds host reads, copies past the staging buffer or
+    // kernels reading beyond it.
+    uint64_t stream_words = 0;
+    {
+        const grid_geom g = make_geom(dims, size);
+        const uint32_t H = g.num_cubes, hdr = header_words(ctx->dtype, H);
+        stream_words = static_cast<uint64_t>(hdr) + make_border(dims, size).count;
+        if (H) {
+            if (length_words < hdr) return NDZB_ERR_CORRUPT_STREAM;
+            const uint32_t *offsets = static_cast<const uint32_t *>(h_stream);
+            const uint32_t bound = ndzb_compressed_cube_bound(ctx->dtype);
+            uint32_t previous = 0;
+            for (uint32_t i = 0; i < H; ++i) {
+                if (offsets[i] < previous || offsets[i] - previous > bound) return NDZB_ERR_CORRUPT_STREAM;
+                previous = offsets[i];
+            }
+            stream_words += previous;
+        }
+        if (stream_words > length_words) return NDZB_ERR_CORRUPT_STREAM;
+    }
+    const size_t in_bytes = static_cast<size_t>(stream_words) * wb;  // what the stream occupies, not all the caller offers
     if (int rc = ensure_buffer(&ctx->d_out, &ctx->d_out_bytes, in_bytes ? in_bytes : 16)) return rc;
     if (int rc = ensure_buffer(&ctx->d_in, &ctx->d_in_bytes, out_bytes ? out_bytes : 16)) return rc;
     {
@@ -766,8 +817,11 @@ int ndzb_offload_decompress(ndzb_ctx *ctx, const void *h_stream, uint32_t length
         if (g.num_cubes > 0 && make_border(dims, size).count == 0 && out_bytes >= pipeline_min_bytes() && !getenv("NDZB_NO_PIPELINE")) {
             const chunk_plan plan = plan_chunks(dims, size, g, wb);
             if (plan.chunks > 1) {
-                const int rc = pipelined_decompress(ctx, h_stream, h_data, dims, size, kernel_ns, g, plan);
+                uint64_t ns = 0;
+                const int rc = pipelined_decompress(ctx, h_stream, h_data, dims, size, (kernel_ns || verbose()) ? &ns : nullptr, g, plan);
                 ctx->last_launches = static_cast<uint32_t>(plan.chunks);
+                if (kernel_ns) *kernel_ns = ns;
+                if (rc == NDZB_OK) report_kernel_time(ns);
                 if (rc == NDZB_OK && consumed_words) {
                     const uint32_t H = g.num_cubes;
                     *consumed_words = header_words(ctx->dtype, H) + static_cast<const uint32_t *>(h_stream)[H - 1];
@@ -782,10 +836,12 @@ int ndzb_offload_decompress(ndzb_ctx *ctx, const void *h_stream, uint32_t length
     NDZB_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
     if (out_bytes) NDZB_CUDA(cudaMemcpyAsync(h_data, ctx->d_in, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     NDZB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (kernel_ns) {
+    if (kernel_ns || verbose()) {
         float ms = 0;
         NDZB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
-        *kernel_ns = static_cast<uint64_t>(static_cast<double>(ms) * 1e6);
+        const uint64_t ns = static_cast<uint64_t>(static_cast<double>(ms) * 1e6);
+        if (kernel_ns) *kernel_ns = ns;
+        report_kernel_time(ns);
     }
     if (consumed_words) {
         // header + last offset + border (reference cuda_codec.inl:740-745); the header lives in host memory
@@ -825,6 +881,7 @@ const char *ndzb_strerror(int status) {
         case NDZB_ERR_CAPACITY: return "more hypercubes than the context was created for";
         case NDZB_ERR_CUDA: return "CUDA error";
         case NDZB_ERR_ALLOC: return "out of memory";
+        case NDZB_ERR_CORRUPT_STREAM: return "compressed input ends inside a stream or its header is corrupt";
         default: return "unknown ndzb status";
     }
 }

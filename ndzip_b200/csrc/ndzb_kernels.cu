@@ -1123,7 +1123,13 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
         ptx::fence_mbar_init();
     }
     __syncthreads();
-    auto bulk_ok = [&](uint32_t t) { return t + 1 < a.count; };
+    // The bulk copy also rounds its source DOWN to 16 bytes: harmless inside the stream (it re-reads the tail of the previous
+    // cube or of the header), but for the stream's very first cube behind a header shorter than that shift it would
+    // read in front of the caller's buffer (the reference API only asks for word alignment): that cube takes the
+    // per-thread path too.
+    const bool first_cube_unsafe = a.hc_begin == 0
+            && (reinterpret_cast<uintptr_t>(stream_cubes) & ~static_cast<uintptr_t>(15)) < reinterpret_cast<uintptr_t>(a.offsets);
+    auto bulk_ok = [&](uint32_t t) { return t + 1 < a.count && !(first_cube_unsafe && t == 0); };
     auto copy_in = [&](uint32_t *buf, uint64_t *bar, uint32_t t, uint32_t begin, uint32_t end) {
         if (bulk_ok(t)) {
             if (tid == 0) {

@@ -414,6 +414,9 @@ def read_sharded(path: str, rank: int = 0, world_size: int = 1):
     with open(path, "rb") as f:
         head = f.read(4 * _FIXED_WORDS)
         count = int(np.frombuffer(head, dtype=np.uint32)[7]) if len(head) == 4 * _FIXED_WORDS else 0
+        # the count comes from the file: never read more table than the file can hold
+        import os
+        count = min(count, max(0, os.fstat(f.fileno()).st_size - len(head)) // (4 * _SEGMENT_WORDS) + 1)
         head += f.read(4 * _SEGMENT_WORDS * count)
         hdr = decode_sharded_header(head)
         bits = np.uint32 if hdr.dtype == "float32" else np.uint64
@@ -426,3 +429,107 @@ def read_sharded(path: str, rank: int = 0, world_size: int = 1):
                 raise ValueError("truncated sharded stream")
             out.append((seg.slab, hdr.slab_shape(i), np.frombuffer(raw, dtype=bits)))
     return hdr, out
+
+
+# --------------------------------------------------------------------------------------------------
+# The data plane proper lives in the library (csrc/ndzb_dist.cu, include/ndzip_b200.h ndzb_dist_*): slab
+# compression, the NCCL count exchange on a side stream, the header fix-up kernel and the NCCL gather. This
+# class is its ctypes mirror; torch.distributed is only used to ship the 128-byte NCCL unique id.
+
+def plan(dtype, global_shape: Sequence[int], world_size: int, rank: int):
+    """ndzb_dist_plan: a rank's slab and where its pieces go in the global stream (pure geometry, no GPU)."""
+    import ctypes
+    from . import _lib
+    from .api import _code
+    dims, sz = _lib.size3(global_shape)
+    out = _lib.DistLayout()
+    _lib.check(_lib.load().ndzb_dist_plan(_code(dtype), dims, sz, world_size, rank, ctypes.byref(out)))
+    return out
+
+
+class DistCodec:
+    """One rank of the multi-GPU hot path. Collective constructor (NCCL communicator over the ranks of
+    ``group``, or of the default process group)."""
+
+    def __init__(self, dtype, global_shape: Sequence[int], group=None, stream=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        from .api import _code, _stream_handle
+
+        self._lib = _lib.load()
+        self.dtype = np.dtype(dtype)
+        self.global_shape = tuple(int(x) for x in global_shape)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        dims, sz = _lib.size3(self.global_shape)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.world > 1:
+            if self.rank == 0:
+                _lib.check(self._lib.ndzb_dist_unique_id(uid.data_ptr()))
+            backend = dist.get_backend(group)
+            carrier = uid.cuda() if backend == "nccl" else uid
+            dist.broadcast(carrier, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            uid = carrier.cpu()
+        self._handle = ctypes.c_void_p()
+        _lib.check(self._lib.ndzb_dist_create(ctypes.byref(self._handle), _code(dtype), dims, sz, uid.data_ptr(), self.rank,
+                                               self.world, _stream_handle(stream)))
+        self.layout = _lib.DistLayout()
+        _lib.check(self._lib.ndzb_dist_layout_of(self._handle, self.rank, ctypes.byref(self.layout)))
+        self.slab_shape = tuple(int(self.layout.slab_size[d]) for d in range(dims))
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.ndzb_dist_destroy(self._handle)
+            self._handle = None
+
+    __del__ = close
+
+    def compress(self, d_slab, d_local_stream, d_local_length=None) -> None:
+        from . import _lib
+        from .api import _ptr
+        _lib.check(self._lib.ndzb_dist_compress(self._handle, _ptr(d_slab), _ptr(d_local_stream), _ptr(d_local_length)))
+
+    def decompress(self, d_local_stream, d_slab) -> None:
+        from . import _lib
+        from .api import _ptr
+        _lib.check(self._lib.ndzb_dist_decompress(self._handle, _ptr(d_local_stream), _ptr(d_slab)))
+
+    def wait_exchange(self) -> None:
+        from . import _lib
+        _lib.check(self._lib.ndzb_dist_wait_exchange(self._handle))
+
+    def gather(self, d_local_stream, d_global_stream=None, root: int = 0) -> int:
+        """Collective. Returns the global stream length in words (known on every rank)."""
+        import ctypes
+        from . import _lib
+        from .api import _ptr
+        total = ctypes.c_uint64(0)
+        _lib.check(self._lib.ndzb_dist_gather(self._handle, _ptr(d_local_stream), _ptr(d_global_stream), root, ctypes.byref(total)))
+        return total.value
+
+    def global_header(self):
+        """This rank's slice of the global header as a torch int32 tensor (valid after wait_exchange on the stream)."""
+        import torch
+        n = int(self.layout.local_cubes)
+        ptr = self._lib.ndzb_dist_global_header(self._handle)
+        return _device_view(ptr, n, torch.int32)
+
+    def gathered_lengths(self):
+        import torch
+        return _device_view(self._lib.ndzb_dist_gathered_lengths(self._handle), self.world, torch.int32)
+
+
+def _device_view(ptr: int, n: int, tdtype):
+    """A torch tensor over device memory owned by the library (no copy)."""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    item = torch.tensor([], dtype=tdtype).element_size()
+    typestr = {4: "<i4", 8: "<i8"}[item]
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr) if n else 0, False), "version": 2}
+    return torch.as_tensor(h, device="cuda") if n else torch.empty(0, dtype=tdtype, device="cuda")

@@ -54,3 +54,40 @@ def test_adapter_program_passes(variant):
         exe = _build(variant)
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "PASS" in res.stdout, res.stdout + res.stderr
+
+
+# ---- multi-GPU data plane through the C ABI alone (tests/cpp/dist_test.cc): one process, one thread per GPU ----
+
+DIST_SRC = os.path.join(ROOT, "tests", "cpp", "dist_test.cc")
+
+
+def _build_dist():
+    from ndzip_b200 import build as nzbuild
+    import oracle
+    nzbuild.build()
+    oracle.build("oracle")
+    os.makedirs(BUILD, exist_ok=True)
+    out = os.path.join(BUILD, "dist_test")
+    libdir = os.path.join(ROOT, "ndzip_b200")
+    oradir = os.path.join(ROOT, "oracle")
+    cmd = ["g++", "-std=c++17", "-O1", "-pthread", DIST_SRC, f"-I{ROOT}/include", f"-I{CUDA}/include", "-o", out,
+           f"-L{libdir}", "-lndzip_b200", f"-L{oradir}", "-lndzip_oracle", f"-L{CUDA}/lib64", "-lcudart",
+           f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{oradir}", f"-Wl,-rpath,{CUDA}/lib64"]
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run(cmd, check=True, env=env)
+    return out
+
+
+def test_dist_program_builds():
+    assert os.path.exists(_build_dist())
+
+
+@pytest.mark.gpu
+def test_dist_program_passes_on_all_visible_gpus():
+    """world = every visible GPU (1 on the single-GPU test box: the slab / gather arithmetic with one rank; the
+    N > 1 run is scripts/gpu_multi.sh under `gpurun --gpus N`)."""
+    exe = os.path.join(BUILD, "dist_test")
+    if not os.path.exists(exe):
+        exe = _build_dist()
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "PASS" in res.stdout, res.stdout + res.stderr

@@ -269,7 +269,9 @@ int run(const options &o) {
             if (valid == 0) break;
             uint32_t consumed = 0;
             uint64_t ns = 0;
-            check(ndzb_offload_decompress(ctx, packed.p, static_cast<uint32_t>(valid / word), raw.p, dims, size, &consumed, &ns), "decompress");
+            const int status = ndzb_offload_decompress(ctx, packed.p, static_cast<uint32_t>(valid / word), raw.p, dims, size, &consumed, &ns);
+            if (status == NDZB_ERR_CORRUPT_STREAM) throw io_error("Compressed input ends inside a stream");
+            check(status, "decompress");
             const size_t consumed_bytes = static_cast<size_t>(consumed) * word;
             if (consumed_bytes > valid) throw io_error("Compressed input ends inside a stream");
             out.put(raw.p, array_bytes);
