@@ -93,25 +93,28 @@ def smooth_constants(seed: int, dims: int, modes: int = 6):
     return out
 
 
-def smooth(shape, dtype, seed: int = 0x5EED0002, noise: float = 1e-4, coord_shape=None) -> np.ndarray:
+def smooth(shape, dtype, seed: int = 0x5EED0002, noise: float = 1e-4, coord_shape=None, index_offset: int = 0,
+           threads: int = 1) -> np.ndarray:
     """Turbulence-like field: six sine modes with a k^(-5/3) amplitude
     spectrum, hashed integer wave vectors |m_d| <= k and phases, plus `noise` * u(index), u in [-1,1).
     Evaluated in float64, rounded to ``dtype``. Mid-range ratios (~0.6 for 3D float32).
-    ``coord_shape`` (default: ``shape``) is the extent the coordinates are normalised by, so that the
-    leading rows of a larger grid can be generated on their own."""
+    ``coord_shape`` (default: ``shape``) is the extent the coordinates are normalised by and ``index_offset`` the
+    linear index of element 0, so that any run of rows of a larger grid can be generated on its own; ``threads`` > 1
+    evaluates slabs side by side (numpy releases the GIL inside its loops)."""
     dims = len(shape)
     coord_shape = tuple(coord_shape) if coord_shape is not None else tuple(shape)
     n = _count(shape)
     if n == 0:
         return np.zeros(shape, dtype=dtype)
     modes = smooth_constants(seed, dims)
-    out = np.zeros(n, dtype=np.float64)
+    out = np.empty(n, dtype=dtype)
     strides = [1] * dims
     for d in range(dims - 2, -1, -1):
         strides[d] = strides[d + 1] * int(shape[d + 1])
     step = 1 << 22  # slabs bound the temporaries
-    for lo in range(0, n, step):
-        idx = np.arange(lo, min(n, lo + step), dtype=np.uint64)
+
+    def fill(lo):
+        idx = np.arange(lo, min(n, lo + step), dtype=np.uint64) + np.uint64(index_offset)
         coords = []
         rem = idx
         for d in range(dims):
@@ -125,8 +128,17 @@ def smooth(shape, dtype, seed: int = 0x5EED0002, noise: float = 1e-4, coord_shap
                     arg += wave[d] * coords[d]
             acc += amp * np.sin(2 * np.pi * arg + phase)
         jitter = (splitmix64(idx ^ (np.uint64(seed) << np.uint64(32))) >> np.uint64(11)).astype(np.float64) * 2.0 ** -52 - 1.0
-        out[lo:lo + idx.size] = acc + noise * jitter
-    return out.astype(dtype).reshape(shape)
+        out[lo:lo + idx.size] = (acc + noise * jitter).astype(dtype)
+
+    starts = range(0, n, step)
+    if threads > 1 and len(starts) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            list(pool.map(fill, starts))
+    else:
+        for lo in starts:
+            fill(lo)
+    return out.reshape(shape)
 
 
 def poly(shape, dtype) -> np.ndarray:
