@@ -171,6 +171,14 @@ int ndzb_dist_gather(ndzb_dist *d, const void *d_local_stream, void *d_global_st
 /* NCCL / CUDA error text of the last failing ndzb_dist_* call on this thread. */
 const char *ndzb_dist_last_error(void);
 
+/* Device-side self tests of the scan primitives, the counterpart of the reference's src/test/cuda_bits_test.cu:37-114
+ * (warp scan, hierarchical scan in isolation). ndzb_selftest_lookback runs the decoupled look-back of the compress
+ * kernel over `count` items with the given lengths — mode 0: two-level (float profiles), 1 / 2: windows of 32 / 64
+ * items (double profiles / tuning) — on the context's descriptors and writes base_words + the exclusive prefix sums;
+ * ndzb_selftest_warp_scan writes the per-warp inclusive sums the encoder and decoder warps compute. */
+int ndzb_selftest_lookback(ndzb_ctx *ctx, int mode, const uint32_t *d_lengths, uint32_t count, uint32_t base_words, uint32_t *d_exclusive);
+int ndzb_selftest_warp_scan(ndzb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, uint32_t n);
+
 /* Host-side stream arithmetic (no GPU needed). */
 /* src/ndzip/common.hh:395-412 */
 uint32_t ndzb_num_hypercubes(int dims, const uint32_t *size);

@@ -38,6 +38,8 @@ SYMBOLS = [
     ("ndzb_version", ctypes.c_char_p, []),
     ("ndzb_last_launch_count", _u32, [_vp]),
     ("ndzb_fixup_header_on", _i, [_vp, _vp, _vp, _u32, _vp, _vp, _u32]),
+    ("ndzb_selftest_lookback", _i, [_vp, _i, _vp, _u32, _u32, _vp]),
+    ("ndzb_selftest_warp_scan", _i, [_vp, _vp, _vp, _u32]),
     # multi-GPU data plane
     ("ndzb_dist_plan", _i, [_i, _i, _vp, _i, _i, _vp]),
     ("ndzb_dist_unique_id", _i, [_vp]),

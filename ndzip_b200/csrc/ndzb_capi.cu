@@ -853,6 +853,39 @@ int ndzb_offload_decompress(ndzb_ctx *ctx, const void *h_stream, uint32_t length
     return NDZB_OK;
 }
 
+int ndzb_selftest_lookback(ndzb_ctx *ctx, int mode, const uint32_t *d_lengths, uint32_t count, uint32_t base_words, uint32_t *d_exclusive) {
+    if (!ctx || mode < 0 || mode > 2 || (count && (!d_lengths || !d_exclusive))) return NDZB_ERR_INVALID_ARGUMENT;
+    if (count == 0) return NDZB_OK;
+    const device_guard on_device(ctx->device);
+    if (int rc = ensure_descriptors(ctx, count)) return rc;
+    const uint32_t resident = static_cast<uint32_t>(g_config[ctx->device].num_sms) * 16u;  // all CTAs resident: waiting on earlier tickets cannot deadlock
+    const uint32_t grid = count < resident ? count : resident;
+    unsigned long long *blocks = ctx->d_blocks[ctx->blocks_cur];
+    if (mode == 0) {
+        NDZB_CUDA(cudaMemsetAsync(blocks, 0, (static_cast<size_t>(ctx->desc_capacity) / 32 + 1) * kDescStride * sizeof(unsigned long long), ctx->stream));
+    }
+    const cudaError_t e = launch_selftest_lookback(mode, d_lengths, count, d_exclusive, ctx->d_desc, blocks, ctx->d_counters, ctx->ticket_base,
+            ctx->epoch, base_words, ctx->d_watch, grid, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "selftest_lookback launch");
+    if (mode == 0) {  // leave the array as a compress launch expects it: all zero
+        NDZB_CUDA(cudaMemsetAsync(blocks, 0, (static_cast<size_t>(ctx->desc_capacity) / 32 + 1) * kDescStride * sizeof(unsigned long long), ctx->stream));
+    }
+    ctx->ticket_base += count + grid;  // every CTA draws one ticket beyond `count`
+    if (++ctx->epoch >= (1u << 30)) {
+        NDZB_CUDA(cudaMemsetAsync(ctx->d_desc, 0, static_cast<size_t>(ctx->desc_capacity) * kDescStride * sizeof(uint64_t), ctx->stream));
+        ctx->epoch = 1;
+    }
+    return NDZB_OK;
+}
+
+int ndzb_selftest_warp_scan(ndzb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, uint32_t n) {
+    if (!ctx || (n && (!d_in || !d_out))) return NDZB_ERR_INVALID_ARGUMENT;
+    const device_guard on_device(ctx->device);
+    const cudaError_t e = launch_selftest_warp_scan(d_in, d_out, n, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "selftest_warp_scan launch");
+    return NDZB_OK;
+}
+
 uint32_t ndzb_num_hypercubes(int dims, const uint32_t *size) {
     if (dims < 1 || dims > 3 || !size) return 0;
     return make_geom(dims, size).num_cubes;

@@ -1370,6 +1370,57 @@ __global__ void store_length_kernel(uint32_t *length_out, uint32_t value, const 
     *length_out = value + (plus ? *plus : 0u);
 }
 
+// =====================================================================================================
+// device-side self tests of the scan primitives (counterpart of the reference's src/test/cuda_bits_test.cu:37-114,
+// which tests warp / block / hierarchical scans in isolation): the same look_back / look_back_blocks / warp_inclusive_sum
+// code the compress kernel runs, driven by a list of lengths instead of encoded cubes
+// =====================================================================================================
+
+// One warp per CTA, persistent; ticket order == item order as in the compress kernel. Item t has length lengths[t]; the
+// warp publishes it after a pseudo-random delay (skew between "SMs"), resolves its exclusive offset with the look-back
+// under test and publishes the inclusive one. Mode 0: two-level (blocks of 32), 1 / 2: windows of 32 / 64.
+template<int Mode>
+__global__ void __launch_bounds__(32) selftest_lookback_kernel(const uint32_t *lengths, uint32_t count, uint32_t *exclusive_out, uint64_t *desc,
+        unsigned long long *blocks, uint32_t *ticket, uint32_t ticket_base, uint32_t epoch, uint32_t base, uint32_t *watch) {
+    const int lane = threadIdx.x;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u) - ticket_base;
+        t = __shfl_sync(kFullMask, t, 0);
+        if (t >= count) return;
+        const uint32_t len = lengths[t];
+        const long long until = clock64() + ((t * 2654435761u) >> 20);  // 0 .. 4095 cycles of skew
+        while (clock64() < until) {}
+        if (lane == 0) {
+            ptx::st_relaxed_gpu(desc + static_cast<size_t>(t) * kDescStride, pack_desc(epoch, kStatusAggregate, len));
+            if (Mode == 0) atomicAdd(blocks + static_cast<size_t>(t >> kBlockShift) * kDescStride, static_cast<unsigned long long>(block_contribution(len)));
+        }
+        uint32_t exclusive = base;
+        bool aborted = false;
+        if (t != 0) {
+            if constexpr (Mode == 0) {
+                exclusive = look_back_blocks(desc, reinterpret_cast<const uint64_t *>(blocks), t, epoch, lane, base, watch, &aborted, nullptr);
+            } else {
+                const look_back_window<Mode> first = look_back_load<Mode>(desc, static_cast<int64_t>(t) - 1, epoch, lane, base);
+                exclusive = look_back<Mode>(desc, t, epoch, lane, first, base, watch, &aborted, nullptr);
+            }
+        }
+        if (aborted) return;
+        if (lane == 0) {
+            ptx::st_relaxed_gpu(desc + static_cast<size_t>(t) * kDescStride, pack_desc(epoch, kStatusPrefix, exclusive + len));
+            exclusive_out[t] = exclusive;
+        }
+    }
+}
+
+// out[i] = inclusive sum of in[] over the lanes of i's warp up to i (the scan every encoder / decoder warp runs)
+__global__ void selftest_warp_scan_kernel(const uint32_t *in, uint32_t *out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t v = i < n ? in[i] : 0u;
+    const uint32_t s = warp_inclusive_sum(v, threadIdx.x & 31);
+    if (i < n) out[i] = s;
+}
+
 // ---- kernel tables ----------------------------------------------------------------------------------
 
 using compress_fn = void (*)(const compress_launch, const CUtensorMap);
@@ -1600,6 +1651,21 @@ cudaError_t launch_fixup_header(const uint32_t *local_header, uint32_t *global_h
     if (count == 0) return cudaSuccess;
     const uint32_t blocks = (count + 255) / 256;
     fixup_header_kernel<<<blocks < 592u ? blocks : 592u, 256, 0, stream>>>(local_header, global_header, count, gathered_lengths, overhead_words, rank);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_selftest_lookback(int mode, const uint32_t *lengths, uint32_t count, uint32_t *exclusive_out, uint64_t *desc,
+        unsigned long long *blocks, uint32_t *ticket, uint32_t ticket_base, uint32_t epoch, uint32_t base, uint32_t *watch, uint32_t grid,
+        cudaStream_t stream) {
+    if (mode == 0) selftest_lookback_kernel<0><<<grid, 32, 0, stream>>>(lengths, count, exclusive_out, desc, blocks, ticket, ticket_base, epoch, base, watch);
+    else if (mode == 1) selftest_lookback_kernel<1><<<grid, 32, 0, stream>>>(lengths, count, exclusive_out, desc, blocks, ticket, ticket_base, epoch, base, watch);
+    else selftest_lookback_kernel<2><<<grid, 32, 0, stream>>>(lengths, count, exclusive_out, desc, blocks, ticket, ticket_base, epoch, base, watch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_selftest_warp_scan(const uint32_t *in, uint32_t *out, uint32_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    selftest_warp_scan_kernel<<<(n + 255) / 256, 256, 0, stream>>>(in, out, n);
     return cudaGetLastError();
 }
 

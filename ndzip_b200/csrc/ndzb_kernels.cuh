@@ -96,6 +96,13 @@ cudaError_t launch_fixup_header(const uint32_t *local_header, uint32_t *global_h
         const uint32_t *gathered_lengths, const uint32_t *overhead_words, uint32_t rank, cudaStream_t stream);
 cudaError_t launch_store_length(uint32_t *length_out, uint32_t value, const uint32_t *plus, cudaStream_t stream);
 
+// Self tests of the scan primitives (ndzb_selftest_*): the decoupled look-back over `count` items of the given lengths
+// (mode 0 two-level, 1 / 2 windows of 32 / 64), `grid` persistent one-warp CTAs; the per-warp inclusive sum.
+cudaError_t launch_selftest_lookback(int mode, const uint32_t *lengths, uint32_t count, uint32_t *exclusive_out, uint64_t *desc,
+        unsigned long long *blocks, uint32_t *ticket, uint32_t ticket_base, uint32_t epoch, uint32_t base, uint32_t *watch, uint32_t grid,
+        cudaStream_t stream);
+cudaError_t launch_selftest_warp_scan(const uint32_t *in, uint32_t *out, uint32_t n, cudaStream_t stream);
+
 // TMA tensor map for the compress input tile of (dtype, dims); returns false if the shape / pointer
 // does not meet TMA's alignment rules (caller then uses vec16 or scalar).
 bool tma_compatible(int dtype, int dims, const void *data, const grid_geom &g);

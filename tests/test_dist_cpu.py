@@ -166,3 +166,33 @@ def test_gloo_sharded_write_then_read_with_any_world_size(oracle, tmp_path, dtyp
                 assert back.tobytes() == data[b:e].tobytes()
                 rows += e - b
         assert rows == shape[0]
+
+
+# ---- the library's slab plan (ndzb_dist_plan, pure geometry: runs without a GPU) against this module's layout arithmetic,
+# which the gloo tests above pin against the oracle
+
+@pytest.mark.parametrize("dtype,shape,world", [
+    ("float32", (130, 70, 40), 3), ("float64", (4096 * 5 + 7,), 2), ("float64", (200, 333), 4), ("float32", (16, 16, 16), 5),
+    ("float64", (1024, 1024, 1024), 8), ("float32", (1 << 31,), 8), ("float32", (7,), 2)])
+def test_library_plan_matches_layout_arithmetic(dtype, shape, world):
+    from ndzip_b200 import dist as nzd
+    words = [1000 + 17 * r for r in range(world)]
+    spans = nzd.slab_partition(shape, world)
+    for r in range(world):
+        L = nzd.plan(dtype, shape, world, r)
+        P = nzd.layout_from_counts(dtype, shape, words, r)
+        assert (L.slab_begin, L.slab_end) == spans[r]
+        assert tuple(L.slab_size[: len(shape)]) == P.local_shape
+        assert L.local_cubes == P.local_cubes and L.cube_index_base == P.cube_index_base
+        assert L.local_header_words == P.local_header_words and L.local_border_words == P.local_border
+        assert L.border_base == P.border_base and L.global_cubes == P.global_cubes
+        assert L.global_header_words == P.global_header_words and L.global_border_words == P.total_border
+
+
+def test_library_plan_rejects_bad_arguments():
+    from ndzip_b200 import NdzipB200Error
+    from ndzip_b200 import dist as nzd
+    with pytest.raises(NdzipB200Error):
+        nzd.plan("float32", (64, 64), 0, 0)
+    with pytest.raises(NdzipB200Error):
+        nzd.plan("float32", (64, 64), 2, 2)

@@ -467,6 +467,7 @@ LARGE_CASES = [
 def test_large_configs_properties(nz, oracle, dtype, shape):
     import torch
     from bench import make_device_input
+    torch.cuda.empty_cache()  # mem_get_info does not see what torch's caching allocator holds from earlier tests
     free, _ = torch.cuda.mem_get_info()
     itemsize = np.dtype(dtype).itemsize
     n_bytes = int(np.prod(shape)) * itemsize
@@ -515,6 +516,27 @@ def test_large_configs_properties(nz, oracle, dtype, shape):
     torch.cuda.synchronize()
     assert int(d_len.cpu().numpy().view(np.uint32)[0]) == n
     assert torch.equal(d_stream[:n], d_stream2[:n])
+    del d_stream2
+    # the WHOLE 8 GiB stream against the reference's own CUDA encoder (its device API is safe up to 2^32 - 1 elements,
+    # SURVEY.md §3.3; the CPU reference would take minutes here), and the reference decoding OUR stream
+    from oracle import ReferenceCuda
+    if ReferenceCuda.available():
+        torch.cuda.empty_cache()
+        free, _ = torch.cuda.mem_get_info()
+        scratch = nz.num_hypercubes(shape) * (4096 + 128) * itemsize  # the reference's chunk scratch, cuda_codec.inl:543-552
+        if free > bound * itemsize + scratch + n_bytes + (4 << 30):
+            rc = ReferenceCuda(dtype, shape)
+            r_stream = torch.zeros(bound, dtype=tbits, device="cuda")
+            r_len = torch.zeros(1, dtype=torch.int32, device="cuda")
+            rc.compress(d_in.data_ptr(), r_stream.data_ptr(), r_len.data_ptr())
+            torch.cuda.synchronize()
+            assert int(r_len.cpu().numpy().view(np.uint32)[0]) == n
+            assert torch.equal(r_stream[:n], d_stream[:n])
+            del r_stream
+            r_back = torch.empty_like(d_in)
+            rc.decompress(d_stream.data_ptr(), r_back.data_ptr())
+            torch.cuda.synchronize()
+            assert torch.equal(r_back.view(tbits), d_in.view(tbits))
 
 
 @pytest.mark.parametrize("dtype,shape", [("float32", (96, 64, 80)), ("float64", (300, 200)), ("float32", (9 * 4096 + 77,))])
@@ -526,6 +548,9 @@ def test_sharded_container_of_gpu_streams(nz, dtype, shape):
     data = synth.smooth(shape, dtype, seed=13)
     spans = nzd.slab_partition(shape, 3)
     local = [gpu_compress(np.ascontiguousarray(data[b:e]))[0] for b, e in spans]
+    from oracle import get_oracle
+    for (b, e), got in zip(spans, local):  # the GPU's slab streams are the oracle's, not merely self-consistent
+        assert np.array_equal(got, get_oracle().compress(np.ascontiguousarray(data[b:e])))
     buf = nzd.pack_sharded(dtype, shape, local)
     hdr = nzd.decode_sharded_header(buf)
     for i, (b, e) in enumerate(spans):
@@ -533,3 +558,157 @@ def test_sharded_container_of_gpu_streams(nz, dtype, shape):
         assert back.tobytes() == data[b:e].tobytes()
     whole, _ = gpu_compress(data)
     assert np.array_equal(nzd.to_global_stream(buf), whole)
+    assert np.array_equal(whole, get_oracle().compress(data))
+
+
+# ---- reference "Residual encodings equivalent" (src/test/codec_profile_test.inl:552-729): a cube whose RESIDUALS are
+# engineered to contain all-zero bit columns, all-zero words and fully dense chunks (pattern at :561-567). The GPU kernel
+# fuses transform and encoding, so the input is the oracle's inverse transform of that cube: its residuals are then the
+# engineered cube exactly, and the cube's stream must be the oracle's zero-bit encoding of it, word for word.
+
+@pytest.mark.parametrize("path", ["tma", "vec16", "scalar"])
+@pytest.mark.parametrize("dtype,dims", PROFILES)
+def test_engineered_residual_cube_encodes_like_the_oracle(nz, oracle, dtype, dims, path):
+    from gpu_util import gpu_compress, gpu_decompress, load_path
+    bits = np.uint32 if dtype == "float32" else np.uint64
+    side = {1: 4096, 2: 64, 3: 16}[dims]
+    eng = synth.engineered_cube(bits)
+    values = oracle.block_transform(eng, dims, inverse=True)           # value domain (bit patterns, may be NaNs)
+    assert np.array_equal(oracle.block_transform(values, dims), eng)   # the transform is a bijection
+    data = values.view(dtype).reshape((side,) * dims)
+    with load_path(path):
+        stream, _ = gpu_compress(data)
+    encoded = oracle.zero_bit_encode(eng)
+    hdr = 1  # one cube: one offset word (f64: offset + padding in one 64-bit word)
+    assert stream.size == hdr + encoded.size
+    assert int(stream[:1].view(np.uint32)[0]) == encoded.size
+    assert np.array_equal(stream[hdr:], encoded)
+    assert np.array_equal(stream, oracle.compress(data))
+    back = gpu_decompress(stream, dtype, data.shape)
+    assert back.tobytes() == data.tobytes()
+
+
+# ---- host pointers beyond 4 GiB: the reference's offloader computes byte sizes in 32 bits and re-allocates per call
+# (src/ndzip/cuda_codec.inl:679-685); ndzb_offload_* uses 64-bit sizes and the chunked three-stream pipeline. The stream
+# it returns must be the device API's, and the round trip exact.
+
+def test_offloader_beyond_four_gib(nz):
+    import torch
+    n = (1 << 30) + 3 * 4096                       # 1D f32, 4 GiB + 48 KiB, 262,147 hypercubes
+    shape = (n,)
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    bound = nz.compressed_length_bound("float32", shape)
+    if free < 3 * 4 * n + 2 * 4 * bound + (4 << 30):
+        pytest.skip("needs ~30 GiB of device memory")
+    try:
+        h_in = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        h_stream = torch.empty(bound, dtype=torch.int32, pin_memory=True)
+        h_back = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    except RuntimeError:
+        pytest.skip("cannot pin 13 GiB of host memory on this box")
+    from bench import make_device_input
+    d_in = make_device_input("float32", shape, seed=0x5EED0005)
+    h_in.copy_(d_in)
+    off = nz.make_cuda_offloader("float32", 1)
+    words = off.compress(h_in, shape, h_stream)
+    assert off.kernel_duration_ns and off.kernel_duration_ns > 0
+    consumed = off.decompress(h_stream, words, h_back, shape)
+    assert consumed == words
+    assert torch.equal(h_back.view(torch.int32), h_in.view(torch.int32))
+    # against the device-pointer API on the same data
+    d_stream = torch.empty(bound, dtype=torch.int32, device="cuda")
+    d_len = torch.zeros(1, dtype=torch.int32, device="cuda")
+    nz.make_cuda_compressor("float32", shape).compress(d_in, shape, d_stream, d_len)
+    torch.cuda.synchronize()
+    assert int(d_len.cpu().numpy().view(np.uint32)[0]) == words
+    assert torch.equal(d_stream[:words].cpu(), h_stream[:words])
+
+
+def test_offloader_rejects_truncated_and_corrupt_streams(nz, oracle):
+    # the header is validated on the host before anything reaches the device (include/ndzip_b200.h,
+    # NDZB_ERR_CORRUPT_STREAM): a stream cut short, a header that runs backwards, a cube longer than its bound
+    from ndzip_b200 import NdzipB200Error
+    data = synth.smooth((3 * 4096 + 5,), "float32", seed=3)
+    stream = oracle.compress(data)
+    off = nz.make_cuda_offloader("float32", 1)
+    out = np.empty_like(data)
+    assert off.decompress(stream, stream.size, out, data.shape) == stream.size and out.tobytes() == data.tobytes()
+    for bad_len in (0, 2, stream.size - 1, stream.size - 6):
+        with pytest.raises(NdzipB200Error, match="ends inside a stream"):
+            off.decompress(stream, bad_len, out, data.shape)
+    backwards = stream.copy()
+    backwards[1] = backwards[0] - 1
+    with pytest.raises(NdzipB200Error, match="corrupt"):
+        off.decompress(backwards, backwards.size, out, data.shape)
+    too_long = stream.copy()
+    too_long[0] = 5000
+    with pytest.raises(NdzipB200Error, match="corrupt"):
+        off.decompress(too_long, too_long.size, out, data.shape)
+    # the library is still usable afterwards (no sticky CUDA error)
+    assert off.decompress(stream, stream.size, out, data.shape) == stream.size and out.tobytes() == data.tobytes()
+
+
+def test_misaligned_stream_pointer_with_a_short_header(nz, oracle):
+    # two cubes behind a two-word header in a buffer that starts 4 bytes past a 16-byte boundary: the decoder's bulk copy
+    # must not round the first cube's source down to in front of the buffer (reference API: word alignment only)
+    import torch
+    from gpu_util import to_device
+    data = synth.smooth((2 * 4096,), "float32", seed=9)
+    expect = oracle.compress(data)
+    backing = torch.zeros(expect.size + 8, dtype=torch.int32, device="cuda")
+    for shift in (1, 2, 3):
+        d_stream = backing[shift: shift + expect.size]
+        d_stream.copy_(torch.from_numpy(expect.view(np.int32)).cuda())
+        d_out = torch.zeros(data.shape, dtype=torch.float32, device="cuda")
+        nz.make_cuda_decompressor("float32", 1).decompress(d_stream, d_out, data.shape)
+        torch.cuda.synchronize()
+        assert d_out.cpu().numpy().tobytes() == data.tobytes()
+
+
+# ---- scan primitives in isolation (reference src/test/cuda_bits_test.cu:37-114 tests its warp / hierarchical scans the
+# same way): the compress kernel's decoupled look-back and the warp scan, driven by plain numbers
+
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["two-level", "window32", "window64"])
+@pytest.mark.parametrize("count", [1, 31, 32, 33, 1000, 70001])
+def test_lookback_primitive_is_an_exclusive_scan(nz, mode, count):
+    import torch
+    from ndzip_b200 import _lib
+    rng = np.random.default_rng(count * 3 + mode)
+    lengths = rng.integers(0, 4225, size=count, dtype=np.uint32)
+    lengths[rng.integers(0, count, size=max(1, count // 7))] = 0
+    base = 12345
+    comp = nz.make_cuda_compressor("float32", (4096 * 4,))       # small context: the self test grows the descriptors
+    d_len = torch.from_numpy(lengths.view(np.int32)).cuda()
+    d_out = torch.full((count,), -1, dtype=torch.int32, device="cuda")
+    for _ in range(3):                                            # epochs: stale descriptors must read as invalid
+        _lib.check(comp._lib.ndzb_selftest_lookback(comp._handle, mode, d_len.data_ptr(), count, base, d_out.data_ptr()))
+        torch.cuda.synchronize()
+        expect = (base + np.concatenate([[0], np.cumsum(lengths.astype(np.uint64))[:-1]])).astype(np.uint32)
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint32), expect)
+        d_out.fill_(-1)
+    # the context still compresses correctly afterwards (descriptors, tickets and block words left consistent)
+    from oracle import get_oracle
+    data = synth.smooth((4096 * 4,), "float32", seed=2)
+    d_stream = torch.zeros(nz.compressed_length_bound("float32", data.shape), dtype=torch.int32, device="cuda")
+    d_n = torch.zeros(1, dtype=torch.int32, device="cuda")
+    comp.compress(torch.from_numpy(data).cuda(), data.shape, d_stream, d_n)
+    torch.cuda.synchronize()
+    n = int(d_n.item())
+    assert np.array_equal(d_stream[:n].cpu().numpy().view(np.uint32), get_oracle().compress(data))
+
+
+def test_warp_scan_primitive(nz):
+    import torch
+    from ndzip_b200 import _lib
+    rng = np.random.default_rng(5)
+    v = rng.integers(0, 65, size=1000, dtype=np.uint32)
+    comp = nz.make_cuda_compressor("float32", (4096,))
+    d_in = torch.from_numpy(v.view(np.int32)).cuda()
+    d_out = torch.zeros_like(d_in)
+    _lib.check(comp._lib.ndzb_selftest_warp_scan(comp._handle, d_in.data_ptr(), d_out.data_ptr(), v.size))
+    torch.cuda.synchronize()
+    pad = np.zeros(1024, dtype=np.uint32)
+    pad[:1000] = v
+    expect = np.cumsum(pad.reshape(-1, 32), axis=1).reshape(-1)[:1000]
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), expect.astype(np.uint32))
