@@ -137,6 +137,7 @@ struct ndzb_ctx {
     uint32_t ticket_base = 0;
     uint32_t epoch = 1;
     int forced_path = -1;             // NDZB_LOAD_PATH=tma|vec16|scalar (profiling / tests)
+    int forced_store = -1;            // NDZB_STORE_PATH=tma|vec16|scalar: the decoder's output path (profiling / tests)
     uint32_t *d_watch = nullptr;      // compress_ws_kernel watchdog record (8 words)
     bool ws_check = false;            // NDZB_WS_CHECK=1: synchronise after every launch and report a raised watchdog as an error
     unsigned long long *d_stats = nullptr;  // NDZB_WS_STATS=1: role/wait cycle counters of the Stats kernel variants, printed per launch
@@ -302,8 +303,16 @@ bool store_vectorisable(const ndzb_ctx *ctx, const void *data, const grid_geom &
 
 int enqueue_decompress_range(ndzb_ctx *ctx, const void *stream_cubes, const uint32_t *offsets, void *d_data,
         const grid_geom &g, uint32_t hc_begin, uint32_t count) {
-    const bool vec = store_vectorisable(ctx, d_data, g);
-    int per_sm = g_config[ctx->device].dec_ctas_per_sm[ctx->dtype][ctx->dims - 1][vec ? 1 : 0];
+    // output path: TMA tensor store of the decoded tile where the output is TMA-addressable (16-byte aligned base and
+    // pitch), else element-wise stores; NDZB_STORE_PATH=tma|vec16|scalar overrides (profiling / tests)
+    int store = store_vectorisable(ctx, d_data, g) ? 2 : 0;
+    if (store == 2 && ctx->forced_store >= 0 && ctx->forced_store < 2) store = ctx->forced_store;
+    CUtensorMap out_map{};
+    if (store == 2) {
+        const CUresult r = make_output_tensor_map(&out_map, ctx->dtype, ctx->dims, d_data, g);
+        if (r != CUDA_SUCCESS) return driver_fail(r, "cuTensorMapEncodeTiled (output)");
+    }
+    int per_sm = g_config[ctx->device].dec_ctas_per_sm[ctx->dtype][ctx->dims - 1][store];
     if (ctx->dec_ctas_cap > 0 && per_sm > ctx->dec_ctas_cap) per_sm = ctx->dec_ctas_cap;  // NDZB_DEC_CTAS (tuning)
     const uint64_t resident = static_cast<uint64_t>(per_sm > 0 ? per_sm : 1) * g_config[ctx->device].num_sms;
     const uint32_t grid = static_cast<uint32_t>(count < resident ? count : resident);
@@ -314,7 +323,7 @@ int enqueue_decompress_range(ndzb_ctx *ctx, const void *stream_cubes, const uint
     a.geom = g;
     a.hc_begin = hc_begin;
     a.count = count;
-    const cudaError_t e = launch_decompress(ctx->dtype, ctx->dims, vec, a, grid, ctx->stream);
+    const cudaError_t e = launch_decompress(ctx->dtype, ctx->dims, store, a, store == 2 ? &out_map : nullptr, grid, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(e, "decompress_kernel launch");
     ctx->last_launches += 1;
     return NDZB_OK;
@@ -528,6 +537,11 @@ int ndzb_ctx_create(ndzb_ctx **out_ctx, int dtype, int dims, uint32_t max_hyperc
         if (!strcmp(p, "tma")) ctx->forced_path = 0;
         else if (!strcmp(p, "vec16")) ctx->forced_path = 1;
         else if (!strcmp(p, "scalar")) ctx->forced_path = 2;
+    }
+    if (const char *p = getenv("NDZB_STORE_PATH")) {
+        if (!strcmp(p, "tma")) ctx->forced_store = 2;
+        else if (!strcmp(p, "vec16")) ctx->forced_store = 1;
+        else if (!strcmp(p, "scalar")) ctx->forced_store = 0;
     }
     if (tuning_build()) {  // -DNDZB_TUNING builds only: A/B kernels and variants
         if (const char *p = getenv("NDZB_COMPRESS_KERNEL")) ctx->use_ws = strcmp(p, "v1") != 0;

@@ -1048,6 +1048,8 @@ struct strip {
         }
     }
     __device__ __forceinline__ strip operator+(const strip &o) const { return strip{{v[0] + o.v[0], v[1] + o.v[1]}}; }
+    // the sign rotation undone (reference src/ndzip/common.hh:441-444): what store() then writes is the final value
+    __device__ __forceinline__ strip rotated_back() const { return strip{{rotr1(v[0]), rotr1(v[1])}}; }
     // undo the sign rotation (reference src/ndzip/common.hh:441-444) and write the final values at p
     template<bool Vec>
     __device__ __forceinline__ void emit(Bits *p) const {
@@ -1086,8 +1088,36 @@ __device__ __forceinline__ void stream_in_cube(uint32_t *buf, const Bits *stream
     if (tid >= 32 && tid - 32 < n - tail_begin && tail_begin >= head) ptx::cp_async_4(buf + shift + tail_begin + (tid - 32), src + tail_begin + (tid - 32));
 }
 
-template<typename Bits, int Dims, bool Vec16>
-__global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decompress_kernel(const decompress_launch a) {
+// How the decoded hypercube reaches global memory (reference store_hypercube, src/ndzip/cuda_codec.inl:58-65):
+//   scalar  element-wise stores: any shape / alignment
+//   vec16   8- / 16-byte stores straight from the registers of the last pass (16-byte aligned base and pitch)
+//   tma     the last pass writes the finished, rotated-back values into the shared-memory tile in a layout a tensor map
+//           describes, and ONE thread issues ONE cp.async.bulk.tensor store per cube (UTMASTG): no per-store 64-bit
+//           address arithmetic, 16 shared-memory stores with immediate offsets instead of 16 global stores per thread
+enum class store_path : int { scalar = 0, vec16 = 1, tma = 2 };
+
+template<typename Bits, int Dims>
+__device__ __forceinline__ void issue_tma_store(const uint32_t *tile, const CUtensorMap *map, const grid_geom &g, uint32_t hc) {
+    uint32_t ucz, ucy, ucx;
+    cube_coords<Dims>(g, hc, ucz, ucy, ucx);
+    const int cz = static_cast<int>(ucz), cy = static_cast<int>(ucy), cx = static_cast<int>(ucx);
+    if constexpr (Dims == 1) {
+        if constexpr (sizeof(Bits) == 4) ptx::tma_store_2d(map, tile, 0, cx * 128);   // [rows of 32][32]
+        else ptx::tma_store_3d(map, tile, 0, cx * 128, 0);                             // [half][runs][16]
+    } else if constexpr (Dims == 2) {
+        if constexpr (sizeof(Bits) == 4) ptx::tma_store_3d(map, tile, 0, cx * 2, cy * 64);      // [y][x / 32][32]
+        else ptx::tma_store_4d(map, tile, 0, cx * 2, cy * 64, 0);                               // [half][y][x / 32][16]
+    } else {
+        if constexpr (sizeof(Bits) == 4) ptx::tma_store_3d(map, tile, cx * 16, cy * 16, cz * 16);   // [z][y][x], SWIZZLE_64B
+        else ptx::tma_store_4d(map, tile, cx * 16, cy * 8, cz * 16, 0);                             // [y parity][z][y / 2][x]
+    }
+    ptx::tma_store_commit();
+}
+
+template<typename Bits, int Dims, store_path Out>
+__global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decompress_kernel(const decompress_launch a, const __grid_constant__ CUtensorMap out_map) {
+    constexpr bool Vec16 = Out != store_path::scalar;
+    constexpr bool Tma = Out == store_path::tma;
     using tr = codec_traits<Bits>;
     constexpr int buf_words = decode_plan<Bits>::buffer_bytes / 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1134,6 +1164,7 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
         if (bulk_ok(t)) {
             if (tid == 0) {
                 constexpr uint32_t w32 = sizeof(Bits) / 4;
+                if constexpr (Tma) ptx::tma_store_wait_read();  // the tensor store of the cube that was decoded in this buffer
                 uint32_t len = end - begin;
                 if (len > static_cast<uint32_t>(tr::max_cube_words)) len = tr::max_cube_words;  // corrupt header: stay inside the buffer
                 const uint32_t *src = reinterpret_cast<const uint32_t *>(stream_cubes + begin);
@@ -1144,6 +1175,10 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
                 ptx::bulk_load(buf, src - shift, bytes, bar);
             }
         } else {
+            if constexpr (Tma) {  // (rare path: the last cube of the range) every thread writes the buffer: all wait
+                if (tid == 0) ptx::tma_store_wait_read();
+                __syncthreads();
+            }
             stream_in_cube<Bits>(buf, stream_cubes, begin, end, tid);
             ptx::cp_async_commit();
             if (tid == 0) ptx::mbar_arrive(bar);  // keeps the barrier's phase in step; the data is waited for with cp.async.wait_group
@@ -1160,10 +1195,11 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
         const uint32_t hc = a.hc_begin + t;
         uint32_t *tile = bufs + (k & 1) * buf_words;
         // prefetch: next cube's words into the other buffer (free since the end of the previous iteration),
-        // the cube after that's offsets into registers
-        if (t + gridDim.x < a.count) {
-            copy_in(bufs + ((k + 1) & 1) * buf_words, &aux.in_bar[(k + 1) & 1], t + gridDim.x, __shfl_sync(kFullMask, next_offsets, 0),
-                    __shfl_sync(kFullMask, next_offsets, 1));
+        // the cube after that's offsets into registers. With tensor stores the other buffer is still being read by the
+        // store issued a moment ago: the copy-in is issued a little later, behind the first barrier of the iteration.
+        const uint32_t next_begin = __shfl_sync(kFullMask, next_offsets, 0), next_end = __shfl_sync(kFullMask, next_offsets, 1);
+        if (!Tma && t + gridDim.x < a.count) {
+            copy_in(bufs + ((k + 1) & 1) * buf_words, &aux.in_bar[(k + 1) & 1], t + gridDim.x, next_begin, next_end);
         }
         const uint32_t begin = __shfl_sync(kFullMask, cur_offsets, 0);
         cur_offsets = next_offsets;
@@ -1190,6 +1226,9 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
         const uint32_t inclusive = warp_inclusive_sum(count, lane);
         if (lane == 31) aux.warp_total[warp] = inclusive;
         __syncthreads();
+        if (Tma && t + gridDim.x < a.count) {
+            copy_in(bufs + ((k + 1) & 1) * buf_words, &aux.in_bar[(k + 1) & 1], t + gridDim.x, next_begin, next_end);
+        }
         uint32_t before = 0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
@@ -1241,7 +1280,13 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
         const uint64_t origin = cube_origin<Dims>(a.geom, hc);
         using S = strip<Bits>;
 
-        if constexpr (Dims == 1) {
+        if constexpr (Dims == 1 && Tma) {
+            // ---- rotate back in registers, run -> tile (the layout the tensor map describes), one tensor store ----
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = rotr1(r[j]);
+            store_run(tile, tid, r);
+            ptx::fence_proxy_async_smem();
+        } else if constexpr (Dims == 1) {
             // ---- rotate back and store, coalesced through the tile (reference cuda_codec.inl:58-65) ----
             store_run(tile, tid, r);
             __syncthreads();
@@ -1280,12 +1325,19 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
             __syncthreads();
             S carry{{0, 0}};
             for (int sg = 0; sg < seg; ++sg) carry = carry + S{{aux.segment_total[sg][2 * xq], aux.segment_total[sg][2 * xq + 1]}};
-            char *dst = reinterpret_cast<char *>(data + origin + static_cast<uint64_t>(seg * 16) * a.geom.n[2] + xq * 2);
-            const uint64_t row_bytes = static_cast<uint64_t>(a.geom.n[2]) * sizeof(Bits);
+            if constexpr (Tma) {
+                // final values back into the tile, in place (every thread rewrites exactly the strips it read)
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                (q[k] + carry).template emit<Vec16>(reinterpret_cast<Bits *>(dst));
-                dst += row_bytes;
+                for (int k = 0; k < 16; ++k) (q[k] + carry).rotated_back().store(tile + col.at(k));
+                ptx::fence_proxy_async_smem();
+            } else {
+                char *dst = reinterpret_cast<char *>(data + origin + static_cast<uint64_t>(seg * 16) * a.geom.n[2] + xq * 2);
+                const uint64_t row_bytes = static_cast<uint64_t>(a.geom.n[2]) * sizeof(Bits);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    (q[k] + carry).template emit<Vec16>(reinterpret_cast<Bits *>(dst));
+                    dst += row_bytes;
+                }
             }
         } else {
             // ---- y direction in the tile, z direction fused with rotate + store; 16 x 8 strips per pass -
@@ -1309,6 +1361,25 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
                 S q[16];
 #pragma unroll
                 for (int z = 0; z < 16; ++z) q[z] = S::load(tile + col.at(z));
+                if constexpr (Tma) {
+#pragma unroll
+                    for (int z = 1; z < 16; ++z) q[z] = q[z] + q[z - 1];
+                    if constexpr (sizeof(Bits) == 8) {
+                        // double: the value tile already has the layout of the tensor map ([y parity][z][y / 2][x], SWIZZLE_128B):
+                        // in place, every thread rewrites the strips it read
+#pragma unroll
+                        for (int z = 0; z < 16; ++z) q[z].rotated_back().store(tile + col.at(z));
+                    } else {
+                        // float: the passes use a layout with the z parity in the swizzle (tile3_unit), which no tensor map can
+                        // describe; the finished values are re-laid out as plain [z][y][x] rows of 64 bytes under SWIZZLE_64B
+                        // once everybody has read its column
+                        __syncthreads();
+                        uint32_t *out = tile + o * 16 + (((xq >> 1) ^ ((o >> 1) & 3)) << 2) + ((xq & 1) << 1);
+#pragma unroll
+                        for (int z = 0; z < 16; ++z) q[z].rotated_back().store(out + z * 256);
+                    }
+                    ptx::fence_proxy_async_smem();
+                } else {
                 // one byte pointer advanced by the plane pitch (a 64-bit add per store) instead of an element index
                 // that is multiplied out and scaled for every store (IMAD.WIDE + LEA + LEA.HI.X)
                 const uint64_t plane_bytes = static_cast<uint64_t>(a.geom.n[1]) * a.geom.n[2] * sizeof(Bits);
@@ -1320,9 +1391,16 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
                     dst += plane_bytes;
                     q[z].template emit<Vec16>(reinterpret_cast<Bits *>(dst));
                 }
+                }
             }
         }
         __syncthreads();  // tile is reused by the cube after next; segment totals by the next cube
+        if constexpr (Tma) {
+            if (tid == 0) issue_tma_store<Bits, Dims>(tile, &out_map, a.geom, hc);  // everybody's writes + proxy fences are behind the barrier
+        }
+    }
+    if constexpr (Tma) {
+        if (tid == 0) ptx::tma_store_wait_all();  // shared memory must outlive the stores that read it
     }
 }
 
@@ -1424,7 +1502,7 @@ __global__ void selftest_warp_scan_kernel(const uint32_t *in, uint32_t *out, uin
 // ---- kernel tables ----------------------------------------------------------------------------------
 
 using compress_fn = void (*)(const compress_launch, const CUtensorMap);
-using decompress_fn = void (*)(const decompress_launch);
+using decompress_fn = void (*)(const decompress_launch, const CUtensorMap);
 
 template<typename Bits, int Dims>
 compress_fn compress_for(load_path p) {
@@ -1445,14 +1523,18 @@ compress_fn compress_entry(int dtype, int dims, load_path p) {
     return dims == 1 ? compress_for<uint64_t, 1>(p) : dims == 2 ? compress_for<uint64_t, 2>(p) : compress_for<uint64_t, 3>(p);
 }
 template<typename Bits, int Dims>
-decompress_fn decompress_for(bool vec) {
-    return vec ? decompress_kernel<Bits, Dims, true> : decompress_kernel<Bits, Dims, false>;
-}
-decompress_fn decompress_entry(int dtype, int dims, bool vec) {
-    if (dtype == 0) {
-        return dims == 1 ? decompress_for<uint32_t, 1>(vec) : dims == 2 ? decompress_for<uint32_t, 2>(vec) : decompress_for<uint32_t, 3>(vec);
+decompress_fn decompress_for(int out) {
+    switch (out) {
+        case 2: return decompress_kernel<Bits, Dims, store_path::tma>;
+        case 1: return decompress_kernel<Bits, Dims, store_path::vec16>;
+        default: return decompress_kernel<Bits, Dims, store_path::scalar>;
     }
-    return dims == 1 ? decompress_for<uint64_t, 1>(vec) : dims == 2 ? decompress_for<uint64_t, 2>(vec) : decompress_for<uint64_t, 3>(vec);
+}
+decompress_fn decompress_entry(int dtype, int dims, int out) {
+    if (dtype == 0) {
+        return dims == 1 ? decompress_for<uint32_t, 1>(out) : dims == 2 ? decompress_for<uint32_t, 2>(out) : decompress_for<uint32_t, 3>(out);
+    }
+    return dims == 1 ? decompress_for<uint64_t, 1>(out) : dims == 2 ? decompress_for<uint64_t, 2>(out) : decompress_for<uint64_t, 3>(out);
 }
 
 using compress_ws_fn = void (*)(const compress_launch, const CUtensorMap);
@@ -1574,8 +1656,8 @@ cudaError_t configure_kernels(kernel_config &cfg) {
                         static_cast<int>(compress_ws_smem(dtype)));
                 if (err != cudaSuccess) return err;
             }
-            for (int v = 0; v < 2; ++v) {
-                auto fn = decompress_entry(dtype, dims, v != 0);
+            for (int v = 0; v < 3; ++v) {
+                auto fn = decompress_entry(dtype, dims, v);
                 err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(decompress_smem(dtype)));
                 if (err != cudaSuccess) return err;
                 err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
@@ -1604,9 +1686,10 @@ cudaError_t launch_compress_ws(int dtype, int dims, int variant, const compress_
     return cudaGetLastError();
 }
 
-cudaError_t launch_decompress(int dtype, int dims, bool vec_store, const decompress_launch &args, uint32_t grid,
+cudaError_t launch_decompress(int dtype, int dims, int store, const decompress_launch &args, const CUtensorMap *out_map, uint32_t grid,
         cudaStream_t stream) {
-    decompress_entry(dtype, dims, vec_store)<<<grid, kCubeThreads, decompress_smem(dtype), stream>>>(args);
+    static const CUtensorMap dummy{};
+    decompress_entry(dtype, dims, store)<<<grid, kCubeThreads, decompress_smem(dtype), stream>>>(args, out_map ? *out_map : dummy);
     return cudaGetLastError();
 }
 
@@ -1753,6 +1836,63 @@ CUresult make_input_tensor_map(CUtensorMap *map, int dtype, int dims, const void
     }
     return encode(map, type, rank, const_cast<void *>(data), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+// Tensor map of the decoder's output tile (the value tile as the last pass leaves it), per profile:
+//   float 1D / 2D  the input views ([rows][32] / [y][x / 32][32], SWIZZLE_128B): the decoder's run rows
+//   float 3D       plain [z][y][x], box 16 x 16 x 16, 64-byte rows under SWIZZLE_64B (re-laid out by the last pass)
+//   double         the two 16 KiB half regions as the slowest view dimension, so that ONE store covers both
+CUresult make_output_tensor_map(CUtensorMap *map, int dtype, int dims, const void *data, const grid_geom &g) {
+    const auto encode = get_encode_tiled();
+    if (!encode) return CUDA_ERROR_NOT_SUPPORTED;
+    const uint64_t n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+    cuuint64_t gdim[5] = {1, 1, 1, 1, 1};
+    cuuint64_t gstride[4] = {16, 16, 16, 16};
+    cuuint32_t box[5] = {1, 1, 1, 1, 1};
+    cuuint32_t estride[5] = {1, 1, 1, 1, 1};
+    cuuint32_t rank = 0;
+    CUtensorMapDataType type;
+    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+    if (dtype == 0) {
+        type = CU_TENSOR_MAP_DATA_TYPE_UINT32;
+        if (dims == 1) {
+            rank = 2;
+            gdim[0] = 32; gdim[1] = n2 / 32;
+            gstride[0] = 128;
+            box[0] = 32; box[1] = 128;
+        } else if (dims == 2) {
+            rank = 3;
+            gdim[0] = 32; gdim[1] = n2 / 32; gdim[2] = n1;
+            gstride[0] = 128; gstride[1] = n2 * 4;
+            box[0] = 32; box[1] = 2; box[2] = 64;
+        } else {
+            rank = 3;
+            gdim[0] = n2; gdim[1] = n1; gdim[2] = n0;
+            gstride[0] = n2 * 4; gstride[1] = n1 * n2 * 4;
+            box[0] = 16; box[1] = 16; box[2] = 16;
+            swizzle = CU_TENSOR_MAP_SWIZZLE_64B;
+        }
+    } else {
+        type = CU_TENSOR_MAP_DATA_TYPE_UINT64;
+        if (dims == 1) {            // [half][runs][16]
+            rank = 3;
+            gdim[0] = 16; gdim[1] = n2 / 32; gdim[2] = 2;
+            gstride[0] = 256; gstride[1] = 128;
+            box[0] = 16; box[1] = 128; box[2] = 2;
+        } else if (dims == 2) {     // [half][y][x / 32][16]
+            rank = 4;
+            gdim[0] = 16; gdim[1] = n2 / 32; gdim[2] = n1; gdim[3] = 2;
+            gstride[0] = 256; gstride[1] = n2 * 8; gstride[2] = 128;
+            box[0] = 16; box[1] = 2; box[2] = 64; box[3] = 2;
+        } else {                    // [y parity][z][y / 2][x]
+            rank = 4;
+            gdim[0] = n2; gdim[1] = n1 / 2; gdim[2] = n0; gdim[3] = 2;
+            gstride[0] = n2 * 16; gstride[1] = n1 * n2 * 8; gstride[2] = n2 * 8;
+            box[0] = 16; box[1] = 8; box[2] = 16; box[3] = 2;
+        }
+    }
+    return encode(map, type, rank, const_cast<void *>(data), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
 }  // namespace ndzb

@@ -60,7 +60,7 @@ struct decompress_launch {
 struct kernel_config {
     int num_sms = 0;
     int ctas_per_sm[2][3][3] = {};  // [dtype][dims-1][load_path] occupancy of the compress kernels
-    int dec_ctas_per_sm[2][3][2] = {};  // [dtype][dims-1][vectorised store?]
+    int dec_ctas_per_sm[2][3][3] = {};  // [dtype][dims-1][store path: scalar / vec16 / tma]
 };
 
 // Queries occupancy and opts the kernels into their dynamic shared memory size. Returns cudaError_t.
@@ -79,7 +79,8 @@ bool tuning_build();  // compiled with -DNDZB_TUNING (variants 1-4, statistics, 
 bool compress_ws_uses_blocks(int dtype, int variant);  // two-level look-back: needs block_desc / block_desc_next
 cudaError_t launch_compress_ws(int dtype, int dims, int variant, const compress_launch &args, const CUtensorMap &in_map,
         uint32_t grid, cudaStream_t stream);
-cudaError_t launch_decompress(int dtype, int dims, bool vec_store, const decompress_launch &args, uint32_t grid,
+// store: 0 element-wise, 1 vectorised LSU stores, 2 TMA tensor store of the decoded tile (needs out_map)
+cudaError_t launch_decompress(int dtype, int dims, int store, const decompress_launch &args, const CUtensorMap *out_map, uint32_t grid,
         cudaStream_t stream);
 
 // Border: stream_border[i] = bits(data[border_linear_index(i)]) and the inverse.
@@ -108,5 +109,7 @@ cudaError_t launch_selftest_warp_scan(const uint32_t *in, uint32_t *out, uint32_
 bool tma_compatible(int dtype, int dims, const void *data, const grid_geom &g);
 // Fills `map`; returns CUDA_SUCCESS or the driver error.
 CUresult make_input_tensor_map(CUtensorMap *map, int dtype, int dims, const void *data, const grid_geom &g);
+// Tensor map of the decoder's output tile (same alignment rules: tma_compatible).
+CUresult make_output_tensor_map(CUtensorMap *map, int dtype, int dims, const void *data, const grid_geom &g);
 
 }  // namespace ndzb

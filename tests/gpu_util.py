@@ -9,19 +9,24 @@ import ndzip_b200 as nz
 
 @contextmanager
 def load_path(name):
-    """Force the compress input path (tma | vec16 | scalar); read by ndzb_ctx_create."""
-    old = os.environ.get("NDZB_LOAD_PATH")
-    if name is None:
-        os.environ.pop("NDZB_LOAD_PATH", None)
-    else:
-        os.environ["NDZB_LOAD_PATH"] = name
+    """Force the compress input path AND the decompress output path (tma | vec16 | scalar); read by ndzb_ctx_create
+    (NDZB_LOAD_PATH: TMA tensor load / 16-byte loads / element-wise loads; NDZB_STORE_PATH: TMA tensor store of the
+    decoded tile / 8-16-byte stores / element-wise stores)."""
+    keys = ("NDZB_LOAD_PATH", "NDZB_STORE_PATH")
+    old = {k: os.environ.get(k) for k in keys}
+    for k in keys:
+        if name is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = name
     try:
         yield
     finally:
-        if old is None:
-            os.environ.pop("NDZB_LOAD_PATH", None)
-        else:
-            os.environ["NDZB_LOAD_PATH"] = old
+        for k in keys:
+            if old[k] is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = old[k]
 
 
 @contextmanager

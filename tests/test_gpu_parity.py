@@ -578,6 +578,8 @@ def test_engineered_residual_cube_encodes_like_the_oracle(nz, oracle, dtype, dim
     data = values.view(dtype).reshape((side,) * dims)
     with load_path(path):
         stream, _ = gpu_compress(data)
+        back = gpu_decompress(stream, dtype, data.shape)   # the decoder's output path follows `path` too
+    assert back.tobytes() == data.tobytes()
     encoded = oracle.zero_bit_encode(eng)
     hdr = 1  # one cube: one offset word (f64: offset + padding in one 64-bit word)
     assert stream.size == hdr + encoded.size
@@ -712,3 +714,19 @@ def test_warp_scan_primitive(nz):
     pad[:1000] = v
     expect = np.cumsum(pad.reshape(-1, 32), axis=1).reshape(-1)[:1000]
     assert np.array_equal(d_out.cpu().numpy().view(np.uint32), expect.astype(np.uint32))
+
+
+@pytest.mark.parametrize("store", ["tma", "vec16", "scalar"])
+@pytest.mark.parametrize("gen", ["hashed", "smooth", "zeros"])
+@pytest.mark.parametrize("dtype,dims", PROFILES)
+def test_decoder_output_paths_on_tma_compatible_shapes(nz, oracle, dtype, dims, gen, store):
+    # the three ways the decoded cube reaches global memory (TMA tensor store of the tile / vector stores / element-wise)
+    # on bordered shapes whose pitch is 16-byte aligned, decoding the ORACLE's stream; the untouched border of the
+    # output buffer around the cubes must come from the stream's border section, not from the tensor store
+    from gpu_util import gpu_decompress, load_path
+    shape = {1: (7 * 4096 + 124,), 2: (150, 196), 3: (36, 52, 40)}[dims]
+    data = np.zeros(shape, dtype) if gen == "zeros" else synth.make(gen, shape, dtype, seed=23)
+    stream = oracle.compress(data)
+    with load_path(store):
+        back = gpu_decompress(stream, dtype, shape)
+    assert back.tobytes() == data.tobytes()
