@@ -1555,12 +1555,12 @@ struct ws_variant {
 // B200 with descriptors one per 64 bytes (profiles/README.md): float 5 groups + 4 retire warps + two-level look-back
 // (3-D 0.193 ms, 1-D 0.297 ms per GiB), double 3 + 2 with 32-cube windows (2-D 0.199 ms).
 #if defined(NDZB_TUNING)
-constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}, {5, 4, 0, 0, 0, 1, false, false}, {5, 4, 0, 0, 0, 1, true, false},
-        {5, 4, 0, 1, 0, 1, true, false}, {5, 4, 0, 1, 0, 1, false, true}, {5, 5, 0, 1, 0, 1, false, false}, {5, 6, 0, 1, 0, 1, false, false},
-        {5, 5, 0, 0, 0, 1, true, false}};
-constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 2, 1, 0, 0, 1, false, false}, {3, 2, 1, 0, 0, 1, true, false},
-        {3, 2, 1, 1, 0, 1, true, false}, {3, 2, 1, 1, 0, 1, false, true}, {3, 3, 1, 1, 0, 1, false, false}, {3, 4, 1, 1, 0, 1, false, false},
-        {3, 3, 0, 1, 0, 1, false, false}};
+constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}, {6, 3, 0, 1, 0, 1, false, false}, {5, 3, 0, 1, 0, 1, false, false},
+        {4, 4, 0, 1, 0, 1, false, false}, {5, 4, 0, 1, 0, 1, false, true}, {6, 2, 0, 1, 0, 1, false, false}, {4, 5, 0, 1, 0, 1, false, false},
+        {4, 3, 0, 1, 0, 1, false, false}};
+constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 3, 1, 1, 0, 1, false, false}, {3, 2, 0, 1, 0, 1, false, false},
+        {2, 2, 1, 1, 0, 1, false, false}, {3, 2, 1, 1, 0, 1, false, true}, {3, 4, 1, 1, 0, 1, false, false}, {3, 3, 0, 1, 0, 1, false, false},
+        {3, 1, 1, 1, 0, 1, false, false}};
 #else
 #ifndef NDZB_LA
 #define NDZB_LA 1
