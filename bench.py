@@ -365,24 +365,31 @@ def run_dist_config(name, world, rank, dev, steps=5, identity=True):
         return codec.gather(d_stream, d_global, root=0)
 
     def timed(fn, reps):
+        """Median over `reps` individually timed calls on every rank (device events), then the max over ranks; the
+        K-call block time (max over ranks) is returned beside it. (A fresh NCCL communicator's first collectives and the
+        tear-down of the previous one show up as outliers in a plain block average: 1.87 instead of 0.57 ms per step
+        for cfg5 on 8 GPUs when it ran right after cfg4.)"""
         sync_all()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        marks[0].record()
+        for i in range(reps):
             fn()
-        b.record()
+            marks[i + 1].record()
         sync_all()
-        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        each = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(reps))
+        t = torch.tensor([each[len(each) // 2], marks[0].elapsed_time(marks[reps]) / reps], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return float(t[0].item()), float(t[1].item())
 
-    for _ in range(2):
+    for _ in range(5):
         step()
     total_words = step_gather()  # warm-up: NCCL point-to-point connections
+    for _ in range(3):
+        step()
     sync_all()
     roundtrip = bool(torch.equal(d_in.view(tbits), d_back.view(tbits)))
-    ms_step = timed(step, steps)
-    ms_gather = timed(step_gather, max(2, steps // 2))
+    ms_step, ms_step_block = timed(step, max(steps, 9))
+    ms_gather, _ = timed(step_gather, max(3, steps // 2))
     tc = time_call(lambda: codec.compress(d_in, d_stream, d_len), steps)
     codec.wait_exchange()
     torch.cuda.synchronize()
@@ -418,6 +425,8 @@ def run_dist_config(name, world, rank, dev, steps=5, identity=True):
     out = {
         "workload": f"{name}: {desc} x {world} ranks = {global_shape}", "per_rank_bytes": nbytes_rank,
         "value": nbytes_rank * world / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_step,
+        "ms_per_step_block_average": ms_step_block,
+        "timing": "median of individually event-timed steps per rank, max over ranks (block average beside it)",
         "with_gather_gbs": nbytes_rank * world / (ms_gather * 1e-3) / 1e9, "with_gather_ms": ms_gather,
         "global_stream_bytes": int(total_words) * itemsize, "ratio": n_words * itemsize / nbytes_rank,
         "roofline": {"kernel": "compress_ws_kernel", "achieved_per_gpu_avg": float(frac.item()) / world, "peak": peak,
