@@ -199,6 +199,22 @@ load_path choose_path(const ndzb_ctx *ctx, const void *data, const grid_geom &g)
     return load_path::tma;
 }
 
+// After a launch that failed or was abandoned by the watchdog the device-side scan state (ticket counter, totals,
+// look-back descriptors, block words) no longer matches the host's book-keeping: start over from a clean slate.
+int reset_scan_state(ndzb_ctx *ctx) {
+    NDZB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(uint32_t), ctx->stream));
+    if (ctx->d_desc) NDZB_CUDA(cudaMemsetAsync(ctx->d_desc, 0, static_cast<size_t>(ctx->desc_capacity) * kDescStride * sizeof(uint64_t), ctx->stream));
+    for (auto b : ctx->d_blocks) {
+        if (b) NDZB_CUDA(cudaMemsetAsync(b, 0, (static_cast<size_t>(ctx->desc_capacity) / 32 + 1) * kDescStride * sizeof(unsigned long long), ctx->stream));
+    }
+    NDZB_CUDA(cudaMemsetAsync(ctx->d_watch, 0, 7 * sizeof(uint32_t), ctx->stream));  // keeps [7], the mode
+    ctx->ticket_base = 0;
+    ctx->epoch = 1;
+    ctx->blocks_cur = 0;
+    ctx->total_cur = 0;
+    return NDZB_OK;
+}
+
 // Enqueue the compression of cubes [hc_begin, hc_begin + count) (count > 0).
 int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g, uint32_t hc_begin, uint32_t count,
         void *out_cubes, uint32_t *out_offsets, uint32_t *pad_word, uint32_t *length_out, uint32_t length_add,
@@ -226,8 +242,8 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
     // a chained launch starts where the previous one ended: it reads that total from one scalar and writes its own
     // to the other, so the read never races with the write of the launch's last cube
     a.base_words = chained ? ctx->d_counters + 1 + ctx->total_cur : nullptr;
-    ctx->total_cur ^= 1;
-    a.total_words = ctx->d_counters + 1 + ctx->total_cur;
+    const int total_next = ctx->total_cur ^ 1;   // (the host's book-keeping only advances once the launch has succeeded)
+    a.total_words = ctx->d_counters + 1 + total_next;
     a.length_out = length_out;
     a.length_add = length_add;
     a.desc = ctx->d_desc;
@@ -244,10 +260,11 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
             a.block_desc = ctx->d_blocks[ctx->blocks_cur];
             a.block_desc_next = ctx->d_blocks[ctx->blocks_cur ^ 1];
             a.block_words_next = ctx->desc_capacity / 32 + 1;
-            ctx->blocks_cur ^= 1;
         }
         const cudaError_t e = launch_compress_ws(ctx->dtype, ctx->dims, ctx->ws_variant, a, map, grid, ctx->stream);
         if (e != cudaSuccess) return cuda_fail(e, "compress_ws_kernel launch");
+        if (a.block_desc) ctx->blocks_cur ^= 1;
+        ctx->total_cur = total_next;
         ctx->ticket_base += count + compress_ws_ticket_overdraw(ctx->dtype, ctx->ws_variant, grid);  // wraps together with the device counter
         if (ctx->d_stats) {
             unsigned long long h[16];
@@ -280,13 +297,14 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
                         fclose(f);
                     }
                 }
-                NDZB_CUDA(cudaMemset(ctx->d_watch, 0, 7 * sizeof(uint32_t)));  // keeps [7], the mode
+                if (int rc = reset_scan_state(ctx)) return rc;  // the abandoned launch left tickets, descriptors and totals half-written
                 return NDZB_ERR_CUDA;
             }
         }
     } else {
         const cudaError_t e = launch_compress(ctx->dtype, ctx->dims, path, a, &map, grid, ctx->stream);
         if (e != cudaSuccess) return cuda_fail(e, "compress_kernel launch");
+        ctx->total_cur = total_next;
         ctx->ticket_base += count + compress_ticket_overdraw(grid);  // wraps together with the device counter
     }
     ctx->last_launches += 1;
@@ -333,7 +351,7 @@ int enqueue_decompress_range(ndzb_ctx *ctx, const void *stream_cubes, const uint
 // The grid is cut into slabs of whole cube rows along dimension 0. H2D of slab c+1, the kernels of slab c
 // and D2H of slab c-1 run on three streams, so the call is bounded by max(H2D, D2H) over PCIe instead of
 // their sum. Used for border-free extents above a size threshold; everything else takes the simple path.
-constexpr int kMaxChunks = 64;
+constexpr int kMaxChunks = 128;
 constexpr size_t kChunkBytes = size_t{32} << 20;
 constexpr size_t kPipelineMinBytes = size_t{16} << 20;
 
@@ -441,9 +459,15 @@ int pipelined_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uint32
         NDZB_CUDA(cudaMemcpyAsync(ctx->h_totals + c, ctx->d_counters + 1 + ctx->total_cur, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         NDZB_CUDA(cudaEventRecord(ctx->ev_done[c], ctx->stream));
     }
-    // drain: as soon as a chunk's total is known on the host, its cubes go back on the copy-out stream
+    // drain: the compressed cubes go back on the copy-out stream as their totals become known on the host. The copy
+    // sizes are only known there, so every D2H needs one host synchronisation: early chunks are sent in batches of
+    // kDrainBatch (their D2H hides under the H2D of later chunks anyway), the last ones one by one so that little is
+    // left to copy when the last kernel ends.
+    constexpr int kDrainBatch = 8, kDrainTail = 4;
     uint32_t prev = 0;
     for (int c = 0; c < plan.chunks; ++c) {
+        const bool sync_here = plan.chunks - 1 - c < kDrainTail || (c + 1) % kDrainBatch == 0;
+        if (!sync_here) continue;
         NDZB_CUDA(cudaEventSynchronize(ctx->ev_done[c]));
         const uint32_t tot = ctx->h_totals[c];
         const size_t off = (static_cast<size_t>(hdr) + prev) * wb;

@@ -170,6 +170,7 @@ struct ndzb_dist {
     ndzb_ctx *ctx = nullptr;
     ncclComm_t comm = nullptr;
     cudaStream_t stream = nullptr;       // the caller's stream (compress / decompress / gather)
+    bool owns_stream = false;            // ndzb_dist_create_local makes one per rank
     cudaStream_t side = nullptr;         // high priority: count exchange + header fix-up
     cudaEvent_t ev_compressed = nullptr, ev_exchanged = nullptr;
     uint32_t *d_length = nullptr;        // this rank's stream length in words
@@ -268,7 +269,11 @@ int ndzb_dist_create_local(ndzb_dist **out, int dtype, int dims, const uint32_t 
         }
         cudaStream_t s = nullptr;
         if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) rc = fail("cudaStreamCreate", "failed");
-        if (rc == NDZB_OK) rc = dist_init(out[r], dtype, dims, global_size, r, world, s);
+        if (rc == NDZB_OK) {
+            out[r]->owns_stream = true;
+            out[r]->stream = s;  // (dist_init sets it again; kept here so that a failing init still releases it)
+            rc = dist_init(out[r], dtype, dims, global_size, r, world, s);
+        }
     }
     if (rc == NDZB_OK && world > 1) {
         std::vector<ncclComm_t> comms(world);
@@ -291,6 +296,7 @@ void ndzb_dist_destroy(ndzb_dist *d) {
     if (d->comm && nccl().ok) nccl().CommDestroy(d->comm);
     if (d->ctx) ndzb_ctx_destroy(d->ctx);
     if (d->side) cudaStreamDestroy(d->side);
+    if (d->owns_stream && d->stream) cudaStreamDestroy(d->stream);
     if (d->ev_compressed) cudaEventDestroy(d->ev_compressed);
     if (d->ev_exchanged) cudaEventDestroy(d->ev_exchanged);
     if (d->d_length) cudaFree(d->d_length);

@@ -19,6 +19,10 @@ namespace ndzb {
 namespace {
 
 constexpr uint32_t kFullMask = 0xffffffffu;
+// pause between two polls of look-back descriptors that are not published yet
+#ifndef NDZB_POLL_NS
+#define NDZB_POLL_NS 20
+#endif
 // -DNDZB_TUNING builds the A/B scaffolding: tuning variants 1-4 of compress_ws_kernel, its Stats instantiation, the
 // NDZB_WS_DEBUG profiling aids (which emit INVALID streams) and compress_kernel for TMA inputs. The default build
 // carries one compress_ws_kernel per profile and none of the debug branches.
@@ -202,7 +206,7 @@ __device__ __forceinline__ uint32_t look_back(const uint64_t *desc, uint32_t t, 
                 if (aborted) *aborted = true;
                 return 0;
             }
-            __nanosleep(20);
+            __nanosleep(NDZB_POLL_NS);
             if (polls) *polls += 1u;
             s = look_back_load<Depth, Cg>(desc, idx, epoch, lane, base);
         }
@@ -261,7 +265,7 @@ __device__ __forceinline__ uint32_t look_back_blocks(const uint64_t *desc, const
             *aborted = true;
             return 0;
         }
-        __nanosleep(20);
+        __nanosleep(NDZB_POLL_NS);
         if (polls) *polls += 1u;
         if ((need >> lane) & 1u) own = ptx::ld_relaxed_gpu(own_ptr);
     }
@@ -287,7 +291,7 @@ __device__ __forceinline__ uint32_t look_back_blocks(const uint64_t *desc, const
             *aborted = true;
             return 0;
         }
-        __nanosleep(20);
+        __nanosleep(NDZB_POLL_NS);
         if (polls) *polls += 1u;
         if ((need >> lane) & 1u) {
             blk = ptx::ld_relaxed_gpu(block_word(m));
@@ -594,10 +598,11 @@ struct ws_plan {
 
 template<int S, int G>
 struct ws_aux {
-    uint64_t full[S], done[S], empty[S], taken[S], counted[S];
+    uint64_t full[S], done[S], empty[S], resolved[S], counted[S];
     uint32_t ticket[S];
     uint32_t seq[S];    // which of the CTA's cubes the slot holds (guards against mbarrier phase-parity aliasing)
     uint32_t words[S];
+    uint32_t offset[S];  // CP > 0: the cube's exclusive offset, handed from its retire warp to its copy warp
     uint32_t issued[S];  // Stats instantiations: clock (low word) at which the slot's TMA load was issued
     uint32_t freed[S];   //                       clock at which the slot was handed back to the loader
     uint32_t warp_total[2][G][4];
@@ -658,16 +663,16 @@ __device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *ds
     if (w < n) dst[w] = img[w];
 }
 
-template<typename Bits, int Dims, int G, int R, int LB, int LA, int PF, bool Early, bool Dyn, bool Stats>
-__global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
+template<typename Bits, int Dims, int G, int R, int LB, int LA, int CP, bool Early, bool Dyn, bool Stats>
+__global__ void __launch_bounds__((4 * G + 1 + R + CP) * 32, 1)
         compress_ws_kernel(const compress_launch a, const __grid_constant__ CUtensorMap in_map) {
     using tr = codec_traits<Bits>;
     constexpr int S = ws_plan<Bits>::slots;
     constexpr int slot_words = ws_plan<Bits>::slot_bytes / 4;
-    constexpr uint32_t kPoison = G > R ? G : R;  // end markers: one for every group and every retire warp
-    static_assert(S > G && S > R && S >= static_cast<int>(kPoison), "ring too small");
+    constexpr uint32_t kPoison = (G > R ? G : R) > CP ? (G > R ? G : R) : CP;  // end markers: one for every group, retire and copy warp
+    static_assert(S > G && S > R && S > CP && S >= static_cast<int>(kPoison), "ring too small");
     static_assert(sizeof(ws_aux<S, G>) <= ws_plan<Bits>::aux_bytes, "aux area too small");
-    static_assert(PF < S, "prefetch limit must be below the ring size");
+    static_assert(CP == 0 || Early, "copy warps take over behind an early look-back");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint32_t *slots = reinterpret_cast<uint32_t *>(smem_raw);
     auto &aux = *reinterpret_cast<ws_aux<S, G> *>(smem_raw + S * ws_plan<Bits>::slot_bytes);
@@ -679,7 +684,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             ptx::mbar_init(&aux.full[s], 1);
             ptx::mbar_init(&aux.done[s], kCubeThreads);
             ptx::mbar_init(&aux.empty[s], 1);
-            ptx::mbar_init(&aux.taken[s], 1);
+            ptx::mbar_init(&aux.resolved[s], 1);
             ptx::mbar_init(&aux.counted[s], 1);
         }
         aux.next_seq = 0;
@@ -697,7 +702,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
         // Static (cube g, g+G, ... per group) or dynamic assignment (Dyn: the group that becomes free takes the CTA's
         // next cube). With static assignment a tile that lands while its group is still busy waits although other
         // groups idle, and every cube behind it in the stream waits for its length.
-        static_assert(!Dyn || (G >= R && PF == 0), "dynamic assignment: one end marker per group, no prefetch limit");
+        static_assert(!Dyn || (G >= R && CP == 0), "dynamic assignment: one end marker per group");
         int s = g;
         uint32_t parity = 0, flip = 0, seq = g, grabs = 0;
         for (;; seq += G) {
@@ -721,7 +726,6 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             const long long c1 = now();
             st_a += c1 - c0;
             if (Stats) st_d += static_cast<uint32_t>(static_cast<uint32_t>(c1) - aux.issued[s]);  // TMA issued -> encoder starts
-            if (PF > 0 && u == 0) ptx::mbar_arrive(&aux.taken[s]);  // lets the loader go PF cubes ahead of the encoders, no further
             if (!alive) {
                 // watchdog: release siblings that may already stand at the group's barrier, then leave
                 asm volatile("bar.arrive %0, %1;" ::"r"(1 + g), "r"(kCubeThreads) : "memory");
@@ -858,8 +862,6 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
         uint32_t parity = 1;  // parity of the phase of empty[s] that ends the PREVIOUS round (none in round 0)
         bool first_round = true;
         uint32_t poison = 0, seq = 0;
-        int ts = 0;            // slot / parity of the cube PF places back
-        uint32_t tparity = 0;
         const long long l0 = now();
         while (poison < kPoison) {
 #pragma unroll
@@ -869,14 +871,6 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                 if (!first_round && !mbar_wait_watched(&aux.empty[s], parity, a.watch, 0xE017u, static_cast<uint32_t>(s), seq)) return;
                 const long long c1 = now();
                 st_a += c1 - c0;
-                if (PF > 0 && seq >= static_cast<uint32_t>(PF)) {
-                    // just-in-time loading: cube seq-PF must have been started by its encoder group
-                    if (!mbar_wait_watched(&aux.taken[ts], tparity, a.watch, 0x7A4Eu, static_cast<uint32_t>(ts), seq)) return;
-                    if (++ts == S) {
-                        ts = 0;
-                        tparity ^= 1u;
-                    }
-                }
                 st_b += now() - c1;
                 if constexpr (LA == 0) {
                     if (!ended) tk[0] = atomicAdd(a.ticket, 1u) - a.ticket_base;
@@ -919,7 +913,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             atomicAdd(a.stats + 6, static_cast<unsigned long long>(now() - l0));    // loader: total
             atomicAdd(a.stats + 15, static_cast<unsigned long long>(st_c));         // slot freed -> its next TMA load issued
         }
-    } else {
+    } else if (warp < 4 * G + 1 + R) {
         // ----------------------------------------------------------------------------------- retire
         const int rw = warp - (4 * G + 1);
         const uint32_t launch_base = a.base_words ? *a.base_words : 0u;
@@ -937,6 +931,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             st_a += c1 - c0;
             const uint32_t t = aux.ticket[s];
             if (t >= a.count) {
+                if (CP > 0 && lane == 0) ptx::mbar_arrive(&aux.resolved[s]);  // hand the end marker on to the copy warps
                 if ((kNoTicket - t) + R >= kPoison) break;  // the last end marker addressed to this warp
                 s += R;
                 if (s >= S) {
@@ -976,6 +971,21 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
                     if (a.length_out) *a.length_out = a.length_add + after;  // cuda_codec.inl:507-511
                 }
             }
+            if constexpr (CP > 0) {
+                // the offset is known and published: the copy-out is somebody else's job, this warp goes straight to its
+                // next look-back (a look-back that queues behind a 1650-cycle copy holds a slot for nothing)
+                if (lane == 0) {
+                    aux.offset[s] = exclusive;
+                    ptx::mbar_arrive(&aux.resolved[s]);
+                }
+                ++st_n;
+                s += R;
+                if (s >= S) {
+                    s -= S;
+                    parity ^= 1u;
+                }
+                continue;
+            }
             long long c3 = c2;
             if (Early) {
                 // the offset is known; now the image has to be complete (same phase and tag as `counted`)
@@ -1011,6 +1021,39 @@ __global__ void __launch_bounds__((4 * G + 1 + R) * 32, 1)
             atomicAdd(a.stats + 12, static_cast<unsigned long long>(st_polls & 0xffffu));   // look-back: reloads because a predecessor's length was missing
             atomicAdd(a.stats + 13, static_cast<unsigned long long>(st_polls >> 16));       // look-back: windows beyond the first
             atomicAdd(a.stats + 14, static_cast<unsigned long long>(st_d));    // retire (early look-back): waiting for the image after the offset is known
+        }
+    } else {
+        // ------------------------------------------------------------------------------------- copy (CP > 0)
+        // Copy warp c takes the CTA's cubes c, c + CP, ...: once the cube's retire warp has resolved and published its
+        // offset (resolved[s]) and its encoder group has finished the image (done[s]), the image goes to its final stream
+        // position and the slot back to the loader. The retire warps never copy: their next look-back starts at once.
+        const int cw = warp - (4 * G + 1 + R);
+        Bits *out_cubes = static_cast<Bits *>(a.out_cubes);
+        int s = cw;
+        uint32_t parity = 0, seq = cw;
+        constexpr int kStep = CP > 0 ? CP : 1;
+        for (;; seq += kStep) {
+            bool alive = true;
+            do {  // same aliasing guard as in the encoder
+                alive = mbar_wait_watched(&aux.resolved[s], parity, a.watch, 0xC09Eu, static_cast<uint32_t>(s), (seq << 8) | static_cast<uint32_t>(warp));
+            } while (alive && *reinterpret_cast<volatile uint32_t *>(&aux.seq[s]) != seq);
+            if (!alive) break;
+            const uint32_t t = aux.ticket[s];
+            if (t >= a.count) {
+                if ((kNoTicket - t) + kStep >= kPoison) break;  // the last end marker addressed to this warp
+            } else {
+                if (!mbar_wait_watched(&aux.done[s], parity, a.watch, 0xC0D0u, static_cast<uint32_t>(s), (seq << 8) | static_cast<uint32_t>(warp))) break;
+                constexpr uint32_t w32 = sizeof(Bits) / 4;
+                copy_image_out(slots + s * slot_words, reinterpret_cast<uint32_t *>(out_cubes + aux.offset[s]), aux.words[s] * w32, lane);
+                ptx::fence_proxy_async_smem();   // these generic reads before the next TMA load into the slot
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&aux.empty[s]);
+            }
+            s += kStep;
+            if (s >= S) {
+                s -= S;
+                parity ^= 1u;
+            }
         }
     }
 }
@@ -1544,7 +1587,8 @@ using compress_ws_fn = void (*)(const compress_launch, const CUtensorMap);
 struct ws_variant {
     int groups, retire;
     int look_back_depth;  // windows of 32 * depth cubes per round trip (negative: read with ld.global.cg)
-    int ticket_lookahead, prefetch_limit;
+    int ticket_lookahead;
+    int copiers;  // copy warps: 0 = the retire warps copy their cubes out themselves
     int early;  // look-back started when the cube's length is known (1) / when its image is complete (0) / 1 for 3-D profiles only (2)
     bool dynamic;  // encoder groups take the CTA's next cube when they become free (instead of cube g, g+G, ...)
     bool stats;
@@ -1555,12 +1599,12 @@ struct ws_variant {
 // B200 with descriptors one per 64 bytes (profiles/README.md): float 5 groups + 4 retire warps + two-level look-back
 // (3-D 0.193 ms, 1-D 0.297 ms per GiB), double 3 + 2 with 32-cube windows (2-D 0.199 ms).
 #if defined(NDZB_TUNING)
-constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}, {6, 3, 0, 1, 0, 1, false, false}, {5, 3, 0, 1, 0, 1, false, false},
-        {4, 4, 0, 1, 0, 1, false, false}, {5, 4, 0, 1, 0, 1, false, true}, {6, 2, 0, 1, 0, 1, false, false}, {4, 5, 0, 1, 0, 1, false, false},
-        {4, 3, 0, 1, 0, 1, false, false}};
-constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 3, 1, 1, 0, 1, false, false}, {3, 2, 0, 1, 0, 1, false, false},
-        {2, 2, 1, 1, 0, 1, false, false}, {3, 2, 1, 1, 0, 1, false, true}, {3, 4, 1, 1, 0, 1, false, false}, {3, 3, 0, 1, 0, 1, false, false},
-        {3, 1, 1, 1, 0, 1, false, false}};
+constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}, {5, 4, 0, 1, 3, 1, false, false}, {5, 4, 0, 1, 2, 1, false, false},
+        {5, 3, 0, 1, 3, 1, false, false}, {5, 4, 0, 1, 0, 1, false, true}, {4, 4, 0, 1, 4, 1, false, false}, {5, 3, 0, 1, 4, 1, false, false},
+        {5, 5, 0, 1, 2, 1, false, false}};
+constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 2, 1, 1, 2, 1, false, false}, {3, 2, 1, 1, 1, 1, false, false},
+        {3, 3, 1, 1, 2, 1, false, false}, {3, 2, 1, 1, 0, 1, false, true}, {3, 2, 1, 1, 3, 1, false, false}, {3, 3, 1, 1, 3, 1, false, false},
+        {3, 4, 1, 1, 2, 1, false, false}};
 #else
 #ifndef NDZB_LA
 #define NDZB_LA 1
@@ -1575,11 +1619,11 @@ template<typename Bits, int Dims, int V>
 compress_ws_fn compress_ws_variant_fn() {
     if constexpr (sizeof(Bits) == 4) {
         constexpr ws_variant v = kWsVariants32[V];
-        return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.prefetch_limit,
+        return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.copiers,
                 v.early == 1 || (v.early == 2 && Dims == 3), v.dynamic, v.stats>;
     } else {
         constexpr ws_variant v = kWsVariants64[V];
-        return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.prefetch_limit,
+        return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.copiers,
                 v.early == 1 || (v.early == 2 && Dims == 3), v.dynamic, v.stats>;
     }
 }
@@ -1681,7 +1725,7 @@ cudaError_t launch_compress_ws(int dtype, int dims, int variant, const compress_
         uint32_t grid, cudaStream_t stream) {
     if (variant < 0 || variant >= compress_ws_variants(dtype)) variant = 0;
     const ws_variant v = dtype == 0 ? kWsVariants32[variant] : kWsVariants64[variant];
-    const uint32_t threads = static_cast<uint32_t>(4 * v.groups + 1 + v.retire) * 32u;
+    const uint32_t threads = static_cast<uint32_t>(4 * v.groups + 1 + v.retire + v.copiers) * 32u;
     compress_ws_entry(dtype, dims, variant)<<<grid, threads, compress_ws_smem(dtype), stream>>>(args, in_map);
     return cudaGetLastError();
 }
