@@ -431,7 +431,7 @@ def run_dist_config(name, world, rank, dev, steps=5, identity=True):
         "global_stream_bytes": int(total_words) * itemsize, "ratio": n_words * itemsize / nbytes_rank,
         "roofline": {"kernel": "compress_ws_kernel", "achieved_per_gpu_avg": float(frac.item()) / world, "peak": peak,
                      "frac": float(frac.item()) / world / peak, "frac_min_over_ranks": float(frac_min.item()) / peak},
-        "global_stream_identical": identical, "roundtrip_ok": bool(ok.item()),
+        "global_stream_identical": identical, "roundtrip_ok": bool(ok.item()), "gather_path": codec.last_gather_path,
     }
     codec.close()
     del d_in, d_stream, d_back, d_global
@@ -657,8 +657,8 @@ def main():
             del whole, ref, c1
         headline_gather = {"compress_exchange_gather_ms": min(times), "global_stream_bytes": int(total_words) * itemsize,
                            "with_gather_gbs": nbytes_rank * world / (min(times) * 1e-3) / 1e9,
-                           "global_stream_identical": identical,
-                           "note": "ndzb_dist_compress + ndzb_dist_gather (NCCL send/recv into a pre-allocated buffer on rank 0); "
+                           "global_stream_identical": identical, "gather_path": codec.last_gather_path,
+                           "note": "ndzb_dist_compress + ndzb_dist_gather into a pre-allocated buffer on rank 0; "
                                    "bounded by one GPU's NVLink ingest"}
         del d_global
         torch.cuda.empty_cache()

@@ -118,7 +118,7 @@ int ndzb_fixup_header_on(void *cuda_stream, const uint32_t *d_local_header, uint
  * (the reference decoder reads it with the slab's extent). The data path has one exchange step — an ncclAllGather of
  * one uint32 per rank (the stream lengths) on a high-priority side stream, then one kernel that rewrites the rank's
  * "offset_after" header entries (reference src/ndzip/common.hh:342-358) for the global stream — and an optional
- * final gather (ncclSend / ncclRecv straight into place on the root), after which the root holds the stream the
+ * final gather (stores over NVLink peer memory, or ncclSend / ncclRecv, straight into place on the root), after which the root holds the stream the
  * reference produces for the whole grid, bit for bit. NCCL is bound with dlopen("libnccl.so.2") on first use. */
 typedef struct ndzb_dist ndzb_dist;
 #define NDZB_UNIQUE_ID_BYTES 128
@@ -168,6 +168,13 @@ const uint32_t *ndzb_dist_gathered_lengths(const ndzb_dist *d);
  * grid's stream; *global_length_words (nullable, host, every rank) its length. Synchronises the object's stream once
  * (the send / receive sizes must be known on the host), then enqueues the transfers and returns. */
 int ndzb_dist_gather(ndzb_dist *d, const void *d_local_stream, void *d_global_stream, int root, uint64_t *global_length_words);
+/* How the last gather moved the data: 0 = ncclSend / ncclRecv, 1 = stores over NVLink into a CUDA-IPC mapping of the
+ * root's buffer (one process per GPU), 2 = the same with plain pointers (all ranks in one process). The peer-memory
+ * paths need no receive side: every rank copies its header slice, cube segment and border segment straight to their final
+ * offsets, and one 4-byte all-gather behind the copies tells the root's stream that everything has landed. The root
+ * announces the path with a small broadcast; NDZB_GATHER=nccl forces path 0, which is also the fallback when the
+ * buffer has no IPC handle (pool allocations). */
+int ndzb_dist_last_gather_path(const ndzb_dist *d);
 /* NCCL / CUDA error text of the last failing ndzb_dist_* call on this thread. */
 const char *ndzb_dist_last_error(void);
 

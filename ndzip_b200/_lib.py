@@ -55,6 +55,7 @@ SYMBOLS = [
     ("ndzb_dist_gathered_lengths", _vp, [_vp]),
     ("ndzb_dist_gather", _i, [_vp, _vp, _vp, _i, _pu64]),
     ("ndzb_dist_last_error", ctypes.c_char_p, []),
+    ("ndzb_dist_last_gather_path", _i, [_vp]),
 ]
 
 

@@ -14,6 +14,7 @@
 // loaded), so the library has no link-time dependency on it and loads on machines without NCCL.
 #include "../../include/ndzip_b200.h"
 
+#include <cuda.h>  // CUdeviceptr, CUresult (the entry point is fetched at run time)
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -41,6 +42,7 @@ struct nccl_api {
     ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -70,12 +72,13 @@ const nccl_api &nccl() {
         a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(sym("ncclCommInitAll"));
         a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
         a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
+        a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
         a.Send = reinterpret_cast<decltype(a.Send)>(sym("ncclSend"));
         a.Recv = reinterpret_cast<decltype(a.Recv)>(sym("ncclRecv"));
         a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
         a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
         a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
-        a.ok = a.GetUniqueId && a.CommInitRank && a.CommInitAll && a.CommDestroy && a.AllGather && a.Send && a.Recv && a.GroupStart
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommInitAll && a.CommDestroy && a.AllGather && a.Broadcast && a.Send && a.Recv && a.GroupStart
                 && a.GroupEnd && a.GetErrorString;
         return a;
     }();
@@ -179,11 +182,48 @@ struct ndzb_dist {
     uint32_t *d_global_header = nullptr; // this rank's slice of the global header (local_cubes entries)
     uint32_t *h_lengths = nullptr;       // pinned copy of d_lengths for the gather's send / receive sizes
     bool exchange_pending = false;
+    // ---- gather over peer memory (NVLink stores into the root's buffer instead of ncclSend / ncclRecv)
+    bool local_group = false;            // all ranks live in this process (ndzb_dist_create_local): plain pointers are valid
+    struct root_info {                   // what the root tells the other ranks about its destination buffer
+        unsigned char handle[64];        // cudaIpcMemHandle_t of the allocation (mode 1)
+        unsigned long long offset;       // of the buffer inside that allocation (mode 1) / the pointer itself (mode 2)
+        unsigned int mode;               // 0: use NCCL send / recv, 1: CUDA IPC mapping, 2: same process
+        unsigned int pad;
+    };
+    root_info *h_root = nullptr;         // pinned
+    root_info *d_root = nullptr;
+    uint32_t *d_token = nullptr;         // [1 + world]: completion all-gather behind the peer copies
+    struct mapping {
+        unsigned char handle[64];
+        void *base;
+    };
+    std::vector<mapping> mappings;       // IPC mappings opened so far (closed in ndzb_dist_destroy)
 };
 
 namespace {
 
 size_t word_bytes(int dtype) { return dtype == NDZB_F32 ? 4 : 8; }
+
+// base address of the allocation that contains p (cuMemGetAddressRange), 0 if it cannot be determined
+uintptr_t allocation_base(const void *p) {
+    using fn_t = CUresult (*)(CUdeviceptr *, size_t *, CUdeviceptr);
+    static fn_t fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<fn_t>(f);
+    }();
+    if (!fn) return 0;
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, reinterpret_cast<CUdeviceptr>(p)) != CUDA_SUCCESS) return 0;
+    return static_cast<uintptr_t>(base);
+}
+
+bool gather_over_nccl_forced() {
+    const char *env = getenv("NDZB_GATHER");
+    return env && !strcmp(env, "nccl");
+}
 
 int dist_init(ndzb_dist *d, int dtype, int dims, const uint32_t *global_size, int rank, int world, void *cuda_stream) {
     d->dtype = dtype;
@@ -208,6 +248,10 @@ int dist_init(ndzb_dist *d, int dtype, int dims, const uint32_t *global_size, in
     DIST_CUDA(cudaMalloc(&d->d_overhead, world * sizeof(uint32_t)));
     DIST_CUDA(cudaMalloc(&d->d_global_header, (d->layout.local_cubes ? d->layout.local_cubes : 1) * sizeof(uint32_t)));
     DIST_CUDA(cudaHostAlloc(&d->h_lengths, world * sizeof(uint32_t), cudaHostAllocDefault));
+    DIST_CUDA(cudaHostAlloc(&d->h_root, sizeof(ndzb_dist::root_info), cudaHostAllocDefault));
+    DIST_CUDA(cudaMalloc(&d->d_root, sizeof(ndzb_dist::root_info)));
+    DIST_CUDA(cudaMalloc(&d->d_token, (1 + world) * sizeof(uint32_t)));
+    DIST_CUDA(cudaMemset(d->d_token, 0, (1 + world) * sizeof(uint32_t)));
     std::vector<uint32_t> overhead(world);
     for (int r = 0; r < world; ++r) overhead[r] = d->peers[r].local_header_words + static_cast<uint32_t>(d->peers[r].local_border_words);
     DIST_CUDA(cudaMemcpy(d->d_overhead, overhead.data(), world * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -220,6 +264,8 @@ int dist_init(ndzb_dist *d, int dtype, int dims, const uint32_t *global_size, in
 extern "C" {
 
 const char *ndzb_dist_last_error(void) { return g_dist_error; }
+
+int ndzb_dist_last_gather_path(const ndzb_dist *d) { return d && d->h_root && d->world > 1 ? static_cast<int>(d->h_root->mode) : 0; }
 
 int ndzb_dist_unique_id(void *id) {
     if (!id) return NDZB_ERR_INVALID_ARGUMENT;
@@ -270,6 +316,13 @@ int ndzb_dist_create_local(ndzb_dist **out, int dtype, int dims, const uint32_t 
         cudaStream_t s = nullptr;
         if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) rc = fail("cudaStreamCreate", "failed");
         if (rc == NDZB_OK) {
+            out[r]->local_group = true;
+            for (int o = 0; o < world; ++o) {  // peer access for the gather over NVLink (already enabled / unsupported: fine)
+                int can = 0;
+                if (o != r && cudaDeviceCanAccessPeer(&can, devices[r], devices[o]) == cudaSuccess && can) {
+                    if (cudaDeviceEnablePeerAccess(devices[o], 0) != cudaSuccess) cudaGetLastError();
+                }
+            }
             out[r]->owns_stream = true;
             out[r]->stream = s;  // (dist_init sets it again; kept here so that a failing init still releases it)
             rc = dist_init(out[r], dtype, dims, global_size, r, world, s);
@@ -304,6 +357,10 @@ void ndzb_dist_destroy(ndzb_dist *d) {
     if (d->d_overhead) cudaFree(d->d_overhead);
     if (d->d_global_header) cudaFree(d->d_global_header);
     if (d->h_lengths) cudaFreeHost(d->h_lengths);
+    for (auto &m : d->mappings) cudaIpcCloseMemHandle(m.base);
+    if (d->h_root) cudaFreeHost(d->h_root);
+    if (d->d_root) cudaFree(d->d_root);
+    if (d->d_token) cudaFree(d->d_token);
     delete d;
 }
 
@@ -361,6 +418,34 @@ int ndzb_dist_gather(ndzb_dist *d, const void *d_local_stream, void *d_global_st
     if (d->rank == root && !d_global_stream) return NDZB_ERR_INVALID_ARGUMENT;
     const on_device here(d->device);
     DIST_NDZB(ndzb_dist_wait_exchange(d));
+    // The root tells everybody how to reach its buffer: over peer memory (CUDA IPC mapping, or the plain pointer when all
+    // ranks share a process) or, failing that, with NCCL send / recv. One small broadcast on the stream.
+    if (d->world > 1) {
+        if (d->rank == root) {
+            ndzb_dist::root_info info{};
+            if (!gather_over_nccl_forced()) {
+                if (d->local_group) {
+                    info.mode = 2;
+                    info.offset = reinterpret_cast<uintptr_t>(d_global_stream);
+                } else {
+                    const uintptr_t base = allocation_base(d_global_stream);
+                    cudaIpcMemHandle_t h;
+                    if (base && cudaIpcGetMemHandle(&h, reinterpret_cast<void *>(base)) == cudaSuccess) {
+                        static_assert(sizeof h == sizeof info.handle, "cudaIpcMemHandle_t size");
+                        memcpy(info.handle, &h, sizeof h);
+                        info.offset = reinterpret_cast<uintptr_t>(d_global_stream) - base;
+                        info.mode = 1;
+                    } else {
+                        cudaGetLastError();  // e.g. memory from a pool that has no legacy IPC handle: NCCL it is
+                    }
+                }
+            }
+            *d->h_root = info;
+            DIST_CUDA(cudaMemcpyAsync(d->d_root, d->h_root, sizeof info, cudaMemcpyHostToDevice, d->stream));
+        }
+        DIST_NCCL(nccl().Broadcast(d->d_root, d->d_root, sizeof(ndzb_dist::root_info), kNcclUint8, root, d->comm, d->stream));
+        if (d->rank != root) DIST_CUDA(cudaMemcpyAsync(d->h_root, d->d_root, sizeof(ndzb_dist::root_info), cudaMemcpyDeviceToHost, d->stream));
+    }
     // the send / receive sizes have to be known on the host: one 4-byte-per-rank copy and one synchronisation
     DIST_CUDA(cudaMemcpyAsync(d->h_lengths, d->d_lengths, d->world * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
     DIST_CUDA(cudaStreamSynchronize(d->stream));
@@ -397,7 +482,39 @@ int ndzb_dist_gather(ndzb_dist *d, const void *d_local_stream, void *d_global_st
             DIST_CUDA(cudaMemsetAsync(global + static_cast<size_t>(me.global_cubes) * sizeof(uint32_t), 0, sizeof(uint32_t), d->stream));
         }
     }
-    if (d->world > 1) {
+    if (d->world > 1 && d->h_root->mode != 0) {
+        // ---- peer memory: every rank copies its three pieces straight to their final place in the root's buffer over NVLink
+        if (d->rank != root) {
+            char *remote = nullptr;
+            if (d->h_root->mode == 2) {
+                remote = reinterpret_cast<char *>(static_cast<uintptr_t>(d->h_root->offset));
+            } else {
+                void *base = nullptr;
+                for (const auto &m : d->mappings) {
+                    if (memcmp(m.handle, d->h_root->handle, sizeof m.handle) == 0) base = m.base;
+                }
+                if (!base) {
+                    cudaIpcMemHandle_t h;
+                    memcpy(&h, d->h_root->handle, sizeof h);
+                    DIST_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+                    ndzb_dist::mapping m{};
+                    memcpy(m.handle, d->h_root->handle, sizeof m.handle);
+                    m.base = base;
+                    d->mappings.push_back(m);
+                }
+                remote = static_cast<char *>(base) + d->h_root->offset;
+            }
+            const ndzb_dist_layout &me = d->layout;
+            const int r = d->rank;
+            global = remote;  // the *_dst helpers now address the root's buffer
+            if (me.local_cubes) DIST_CUDA(cudaMemcpyAsync(header_dst(r), d->d_global_header, me.local_cubes * sizeof(uint32_t), cudaMemcpyDeviceToDevice, d->stream));
+            if (cube_words[r]) DIST_CUDA(cudaMemcpyAsync(cubes_dst(r), cubes_src(r), cube_words[r] * wb, cudaMemcpyDeviceToDevice, d->stream));
+            if (me.local_border_words) DIST_CUDA(cudaMemcpyAsync(border_dst(r), border_src(r), me.local_border_words * wb, cudaMemcpyDeviceToDevice, d->stream));
+        }
+        // completion: a tiny all-gather behind the copies — it finishes on the root's stream only after every rank has
+        // reached it on its own stream, i.e. after that rank's copies
+        DIST_NCCL(nccl().AllGather(d->d_token, d->d_token + 1, 1, kNcclUint32, d->comm, d->stream));
+    } else if (d->world > 1) {
         DIST_NCCL(nccl().GroupStart());
         ncclResult_t r0 = 0;
         if (d->rank == root) {

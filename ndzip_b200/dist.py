@@ -509,6 +509,12 @@ class DistCodec:
         _lib.check(self._lib.ndzb_dist_gather(self._handle, _ptr(d_local_stream), _ptr(d_global_stream), root, ctypes.byref(total)))
         return total.value
 
+    @property
+    def last_gather_path(self) -> str:
+        """How the last gather moved the data (ndzb_dist_last_gather_path)."""
+        return {0: "nccl send/recv", 1: "peer stores over NVLink (CUDA IPC mapping)", 2: "peer stores over NVLink (same process)"}[
+            self._lib.ndzb_dist_last_gather_path(self._handle)]
+
     def global_header(self):
         """This rank's slice of the global header as a torch int32 tensor (valid after wait_exchange on the stream)."""
         import torch

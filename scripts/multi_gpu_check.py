@@ -35,6 +35,7 @@ def check_case(dtype, shape, rank, world, dev):
     codec.compress(slab, d_stream, d_len)
     d_global = torch.zeros(max(1, int(L.global_bound_words)), dtype=tbits, device=dev) if rank == 0 else None
     total = codec.gather(d_stream, d_global, root=0)
+    path = codec.last_gather_path
     back = torch.empty_like(slab)
     codec.decompress(d_stream, back)
     torch.cuda.synchronize()
@@ -48,7 +49,7 @@ def check_case(dtype, shape, rank, world, dev):
         n = int(ref_len.cpu().numpy().view(np.uint32)[0])
         same = n == total and bool(torch.equal(ref[:n], d_global[:n]))
         ok = ok and same
-        print(f"{dtype} {shape}: global stream {total} words, single-GPU {n} words, identical={same}", flush=True)
+        print(f"{dtype} {shape}: global stream {total} words, single-GPU {n} words, identical={same}, gather via {path}", flush=True)
     codec.close()
     return ok
 
@@ -61,8 +62,13 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ok = True
-    for dtype, shape in CASES:
-        ok = check_case(dtype, shape, rank, world, dev) and ok
+    for gather in ("", "nccl"):  # the gather over NVLink peer memory (default) and over ncclSend / ncclRecv
+        if gather:
+            os.environ["NDZB_GATHER"] = gather
+        else:
+            os.environ.pop("NDZB_GATHER", None)
+        for dtype, shape in CASES:
+            ok = check_case(dtype, shape, rank, world, dev) and ok
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
