@@ -138,6 +138,7 @@ struct ndzb_ctx {
     uint32_t epoch = 1;
     int forced_path = -1;             // NDZB_LOAD_PATH=tma|vec16|scalar (profiling / tests)
     int forced_store = -1;            // NDZB_STORE_PATH=tma|vec16|scalar: the decoder's output path (profiling / tests)
+    bool use_dec_ws = true;           // NDZB_DECOMPRESS_KERNEL=v1: decompress_kernel also where decompress_ws_kernel applies (A/B, tests)
     uint32_t *d_watch = nullptr;      // compress_ws_kernel watchdog record (8 words)
     bool ws_check = false;            // NDZB_WS_CHECK=1: synchronise after every launch and report a raised watchdog as an error
     unsigned long long *d_stats = nullptr;  // NDZB_WS_STATS=1: role/wait cycle counters of the Stats kernel variants, printed per launch
@@ -329,6 +330,20 @@ int enqueue_decompress_range(ndzb_ctx *ctx, const void *stream_cubes, const uint
     if (store == 2) {
         const CUresult r = make_output_tensor_map(&out_map, ctx->dtype, ctx->dims, d_data, g);
         if (r != CUDA_SUCCESS) return driver_fail(r, "cuTensorMapEncodeTiled (output)");
+    }
+    if (store == 2 && ctx->use_dec_ws && decompress_ws_available(ctx->dtype, ctx->dims)) {
+        const uint32_t sms = static_cast<uint32_t>(g_config[ctx->device].num_sms);
+        decompress_launch a{};
+        a.stream_cubes = stream_cubes;
+        a.offsets = offsets;
+        a.data = d_data;
+        a.geom = g;
+        a.hc_begin = hc_begin;
+        a.count = count;
+        const cudaError_t e = launch_decompress_ws(ctx->dims, a, out_map, count < sms ? count : sms, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "decompress_ws_kernel launch");
+        ctx->last_launches += 1;
+        return NDZB_OK;
     }
     int per_sm = g_config[ctx->device].dec_ctas_per_sm[ctx->dtype][ctx->dims - 1][store];
     if (ctx->dec_ctas_cap > 0 && per_sm > ctx->dec_ctas_cap) per_sm = ctx->dec_ctas_cap;  // NDZB_DEC_CTAS (tuning)
@@ -562,6 +577,7 @@ int ndzb_ctx_create(ndzb_ctx **out_ctx, int dtype, int dims, uint32_t max_hyperc
         else if (!strcmp(p, "vec16")) ctx->forced_path = 1;
         else if (!strcmp(p, "scalar")) ctx->forced_path = 2;
     }
+    if (const char *p = getenv("NDZB_DECOMPRESS_KERNEL")) ctx->use_dec_ws = strcmp(p, "v1") != 0;
     if (const char *p = getenv("NDZB_STORE_PATH")) {
         if (!strcmp(p, "tma")) ctx->forced_store = 2;
         else if (!strcmp(p, "vec16")) ctx->forced_store = 1;

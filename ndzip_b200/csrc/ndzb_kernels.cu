@@ -1157,6 +1157,201 @@ __device__ __forceinline__ void issue_tma_store(const uint32_t *tile, const CUte
     ptx::tma_store_commit();
 }
 
+// Decodes ONE hypercube with 128 threads (tid = 0 .. 127): compressed image (shared memory) -> value tile `tile` (which may
+// alias the image) -> global memory (vector / element-wise stores) or, for store_path::tma, the finished tile in the tensor
+// map's layout, fenced for the async proxy: the caller closes with a barrier and issues the tensor store. `sync` is the
+// barrier of the 128 threads (__syncthreads in decompress_kernel, a named barrier in decompress_ws_kernel);
+// `after_first_barrier` runs once behind the first of them (decompress_kernel issues its next copy-in there).
+template<typename Bits, int Dims, store_path Out, typename Sync, typename Hook>
+__device__ __forceinline__ void decode_cube(uint32_t *tile, const uint32_t *image, uint32_t *warp_total, Bits *warp_sum, Bits (*segment_total)[64],
+        const decompress_launch &a, uint32_t hc, int tid, Sync sync, Hook after_first_barrier) {
+    constexpr bool Vec16 = Out != store_path::scalar;
+    constexpr bool Tma = Out == store_path::tma;
+    using tr = codec_traits<Bits>;
+    const int lane = tid & 31, warp = tid >> 5;
+    Bits *data = static_cast<Bits *>(a.data);
+    // ---- chunk heads -> where each chunk's planes start ------------------------------------------------
+    Bits head;
+    uint32_t count;
+    if constexpr (sizeof(Bits) == 4) {
+        head = image[tid];
+        count = popc_bits(head);
+    } else {
+        const int c = tid >> 1;
+        head = (static_cast<uint64_t>(image[2 * c + 1]) << 32) | image[2 * c];
+        count = (tid & 1) == 0 ? popc_bits(head) : 0u;
+    }
+    const uint32_t inclusive = warp_inclusive_sum(count, lane);
+    if (lane == 31) warp_total[warp] = inclusive;
+    sync();
+    after_first_barrier();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        if (w < warp) before += warp_total[w];
+    }
+    uint32_t body = tr::chunks + before + inclusive - count;
+    if constexpr (sizeof(Bits) == 8) body = __shfl_sync(kFullMask, body, lane & ~1);
+
+    // ---- per-thread: planes -> residuals of run `tid`; x-direction prefix sums ------------------
+    Bits r[32];
+    if constexpr (sizeof(Bits) == 4) {
+        run_of_image(image, head, body, r);
+    } else {
+        run_of_image(image, (tid & 1) == 0, head, body, r);
+    }
+    if constexpr (Dims == 3) {
+#pragma unroll
+        for (int i = 1; i < 16; ++i) {
+            r[i] += r[i - 1];
+            r[16 + i] += r[16 + i - 1];
+        }
+    } else {
+#pragma unroll
+        for (int j = 1; j < 32; ++j) r[j] += r[j - 1];
+    }
+    if constexpr (Dims == 1) {
+        // exclusive block scan of the run totals
+        const Bits total = r[31];
+        const Bits incl = warp_inclusive_sum_bits<Bits>(total, lane);
+        if (lane == 31) warp_sum[warp] = incl;
+        sync();
+        Bits carry = incl - total;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            if (w < warp) carry += warp_sum[w];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] += carry;
+    } else if constexpr (Dims == 2) {
+        // a row is two adjacent runs: the right half continues from the left half's total
+        const Bits left = __shfl_up_sync(kFullMask, r[31], 1);
+        if (tid & 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] += left;
+        }
+    }
+    // the value tile aliases the compressed image: everyone must have read before anyone writes
+    sync();
+    const uint64_t origin = cube_origin<Dims>(a.geom, hc);
+    using S = strip<Bits>;
+
+    if constexpr (Dims == 1 && Tma) {
+        // ---- rotate back in registers, run -> tile (the layout the tensor map describes), one tensor store ----
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = rotr1(r[j]);
+        store_run(tile, tid, r);
+        ptx::fence_proxy_async_smem();
+    } else if constexpr (Dims == 1) {
+        // ---- rotate back and store, coalesced through the tile (reference cuda_codec.inl:58-65) ----
+        store_run(tile, tid, r);
+        sync();
+        constexpr int UE = 16 / sizeof(Bits);
+        constexpr int units = kCubeElems / UE;
+        // unit q = tid + 128 i lies 4 UE runs below unit tid: same swizzle, 128 UE words further
+        const uint32_t *unit0 = tile + tile_elem<Bits>(tid * UE);
+#pragma unroll
+        for (int i = 0; i < units / kCubeThreads; ++i) {
+            const int e = (tid + i * kCubeThreads) * UE;
+            const quad v = ld_quad(unit0 + i * (kCubeThreads * UE));
+            if constexpr (sizeof(Bits) == 4) {
+                const quad o{rotr1(v.x), rotr1(v.y), rotr1(v.z), rotr1(v.w)};
+                if constexpr (Vec16) ptx::stg_stream_v4(data + origin + e, uint4{o.x, o.y, o.z, o.w});
+                else { data[origin + e] = o.x; data[origin + e + 1] = o.y; data[origin + e + 2] = o.z; data[origin + e + 3] = o.w; }
+            } else {
+                const uint64_t a0 = rotr1((static_cast<uint64_t>(v.y) << 32) | v.x), a1 = rotr1((static_cast<uint64_t>(v.w) << 32) | v.z);
+                if constexpr (Vec16) ptx::stg_stream_v4(data + origin + e, uint4{static_cast<uint32_t>(a0), static_cast<uint32_t>(a0 >> 32), static_cast<uint32_t>(a1), static_cast<uint32_t>(a1 >> 32)});
+                else { data[origin + e] = a0; data[origin + e + 1] = a1; }
+            }
+        }
+    } else if constexpr (Dims == 2) {
+        // ---- y direction: 32 two-element column strips x four 16-row segments = 128 threads, scanned
+        //      in registers; final values go straight to global memory (no tile write-back)
+        store_run(tile, tid, r);
+        sync();
+        const int xq = tid & 31, seg = tid >> 5;
+        const strip_addr_y2<Bits> col(seg, xq);
+        S q[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) q[k] = S::load(tile + col.at(k));
+#pragma unroll
+        for (int k = 1; k < 16; ++k) q[k] = q[k] + q[k - 1];
+        segment_total[seg][2 * xq] = q[15].v[0];
+        segment_total[seg][2 * xq + 1] = q[15].v[1];
+        sync();
+        S carry{{0, 0}};
+        for (int sg = 0; sg < seg; ++sg) carry = carry + S{{segment_total[sg][2 * xq], segment_total[sg][2 * xq + 1]}};
+        if constexpr (Tma) {
+            // final values back into the tile, in place (every thread rewrites exactly the strips it read)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) (q[k] + carry).rotated_back().store(tile + col.at(k));
+            ptx::fence_proxy_async_smem();
+        } else {
+            char *dst = reinterpret_cast<char *>(data + origin + static_cast<uint64_t>(seg * 16) * a.geom.n[2] + xq * 2);
+            const uint64_t row_bytes = static_cast<uint64_t>(a.geom.n[2]) * sizeof(Bits);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                (q[k] + carry).template emit<Vec16>(reinterpret_cast<Bits *>(dst));
+                dst += row_bytes;
+            }
+        }
+    } else {
+        // ---- y direction in the tile, z direction fused with rotate + store; 16 x 8 strips per pass -
+        store_run3(tile, tid, r);
+        sync();
+        const int xq = tid & 7, o = tid >> 3;  // o = z in the y pass, y in the z pass
+        {
+            const strip_addr_y3<Bits> col(o, xq);
+            S q[16];
+#pragma unroll
+            for (int y = 0; y < 16; ++y) q[y] = S::load(tile + col.at(y));
+#pragma unroll
+            for (int y = 1; y < 16; ++y) {
+                q[y] = q[y] + q[y - 1];
+                q[y].store(tile + col.at(y));
+            }
+        }
+        sync();
+        {
+            const strip_addr_z3<Bits> col(o, xq);
+            S q[16];
+#pragma unroll
+            for (int z = 0; z < 16; ++z) q[z] = S::load(tile + col.at(z));
+            if constexpr (Tma) {
+#pragma unroll
+                for (int z = 1; z < 16; ++z) q[z] = q[z] + q[z - 1];
+                if constexpr (sizeof(Bits) == 8) {
+                    // double: the value tile already has the layout of the tensor map ([y parity][z][y / 2][x], SWIZZLE_128B):
+                    // in place, every thread rewrites the strips it read
+#pragma unroll
+                    for (int z = 0; z < 16; ++z) q[z].rotated_back().store(tile + col.at(z));
+                } else {
+                    // float: the passes use a layout with the z parity in the swizzle (tile3_unit), which no tensor map can
+                    // describe; the finished values are re-laid out as plain [z][y][x] rows of 64 bytes under SWIZZLE_64B
+                    // once everybody has read its column
+                    sync();
+                    uint32_t *out = tile + o * 16 + (((xq >> 1) ^ ((o >> 1) & 3)) << 2) + ((xq & 1) << 1);
+#pragma unroll
+                    for (int z = 0; z < 16; ++z) q[z].rotated_back().store(out + z * 256);
+                }
+                ptx::fence_proxy_async_smem();
+            } else {
+            // one byte pointer advanced by the plane pitch (a 64-bit add per store) instead of an element index
+            // that is multiplied out and scaled for every store (IMAD.WIDE + LEA + LEA.HI.X)
+            const uint64_t plane_bytes = static_cast<uint64_t>(a.geom.n[1]) * a.geom.n[2] * sizeof(Bits);
+            char *dst = reinterpret_cast<char *>(data + origin + static_cast<uint64_t>(o) * a.geom.n[2] + xq * 2);
+            q[0].template emit<Vec16>(reinterpret_cast<Bits *>(dst));
+#pragma unroll
+            for (int z = 1; z < 16; ++z) {
+                q[z] = q[z] + q[z - 1];
+                dst += plane_bytes;
+                q[z].template emit<Vec16>(reinterpret_cast<Bits *>(dst));
+            }
+            }
+        }
+    }
+}
+
 template<typename Bits, int Dims, store_path Out>
 __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decompress_kernel(const decompress_launch a, const __grid_constant__ CUtensorMap out_map) {
     constexpr bool Vec16 = Out != store_path::scalar;
@@ -1255,188 +1450,11 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
         }
         const uint32_t *image = tile + ((reinterpret_cast<uintptr_t>(stream_cubes + begin) >> 2) & 3);
 
-        // ---- chunk heads -> where each chunk's planes start ------------------------------------------------
-        Bits head;
-        uint32_t count;
-        if constexpr (sizeof(Bits) == 4) {
-            head = image[tid];
-            count = popc_bits(head);
-        } else {
-            const int c = tid >> 1;
-            head = (static_cast<uint64_t>(image[2 * c + 1]) << 32) | image[2 * c];
-            count = (tid & 1) == 0 ? popc_bits(head) : 0u;
-        }
-        const uint32_t inclusive = warp_inclusive_sum(count, lane);
-        if (lane == 31) aux.warp_total[warp] = inclusive;
-        __syncthreads();
-        if (Tma && t + gridDim.x < a.count) {
-            copy_in(bufs + ((k + 1) & 1) * buf_words, &aux.in_bar[(k + 1) & 1], t + gridDim.x, next_begin, next_end);
-        }
-        uint32_t before = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            if (w < warp) before += aux.warp_total[w];
-        }
-        uint32_t body = tr::chunks + before + inclusive - count;
-        if constexpr (sizeof(Bits) == 8) body = __shfl_sync(kFullMask, body, lane & ~1);
-
-        // ---- per-thread: planes -> residuals of run `tid`; x-direction prefix sums ------------------
-        Bits r[32];
-        if constexpr (sizeof(Bits) == 4) {
-            run_of_image(image, head, body, r);
-        } else {
-            run_of_image(image, (tid & 1) == 0, head, body, r);
-        }
-        if constexpr (Dims == 3) {
-#pragma unroll
-            for (int i = 1; i < 16; ++i) {
-                r[i] += r[i - 1];
-                r[16 + i] += r[16 + i - 1];
+        decode_cube<Bits, Dims, Out>(tile, image, aux.warp_total, aux.warp_sum, aux.segment_total, a, hc, tid, [] { __syncthreads(); }, [&] {
+            if (Tma && t + gridDim.x < a.count) {
+                copy_in(bufs + ((k + 1) & 1) * buf_words, &aux.in_bar[(k + 1) & 1], t + gridDim.x, next_begin, next_end);
             }
-        } else {
-#pragma unroll
-            for (int j = 1; j < 32; ++j) r[j] += r[j - 1];
-        }
-        if constexpr (Dims == 1) {
-            // exclusive block scan of the run totals
-            const Bits total = r[31];
-            const Bits incl = warp_inclusive_sum_bits<Bits>(total, lane);
-            if (lane == 31) aux.warp_sum[warp] = incl;
-            __syncthreads();
-            Bits carry = incl - total;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                if (w < warp) carry += aux.warp_sum[w];
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] += carry;
-        } else if constexpr (Dims == 2) {
-            // a row is two adjacent runs: the right half continues from the left half's total
-            const Bits left = __shfl_up_sync(kFullMask, r[31], 1);
-            if (tid & 1) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] += left;
-            }
-        }
-        // the value tile aliases the compressed image: everyone must have read before anyone writes
-        __syncthreads();
-        const uint64_t origin = cube_origin<Dims>(a.geom, hc);
-        using S = strip<Bits>;
-
-        if constexpr (Dims == 1 && Tma) {
-            // ---- rotate back in registers, run -> tile (the layout the tensor map describes), one tensor store ----
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = rotr1(r[j]);
-            store_run(tile, tid, r);
-            ptx::fence_proxy_async_smem();
-        } else if constexpr (Dims == 1) {
-            // ---- rotate back and store, coalesced through the tile (reference cuda_codec.inl:58-65) ----
-            store_run(tile, tid, r);
-            __syncthreads();
-            constexpr int UE = 16 / sizeof(Bits);
-            constexpr int units = kCubeElems / UE;
-            // unit q = tid + 128 i lies 4 UE runs below unit tid: same swizzle, 128 UE words further
-            const uint32_t *unit0 = tile + tile_elem<Bits>(tid * UE);
-#pragma unroll
-            for (int i = 0; i < units / kCubeThreads; ++i) {
-                const int e = (tid + i * kCubeThreads) * UE;
-                const quad v = ld_quad(unit0 + i * (kCubeThreads * UE));
-                if constexpr (sizeof(Bits) == 4) {
-                    const quad o{rotr1(v.x), rotr1(v.y), rotr1(v.z), rotr1(v.w)};
-                    if constexpr (Vec16) ptx::stg_stream_v4(data + origin + e, uint4{o.x, o.y, o.z, o.w});
-                    else { data[origin + e] = o.x; data[origin + e + 1] = o.y; data[origin + e + 2] = o.z; data[origin + e + 3] = o.w; }
-                } else {
-                    const uint64_t a0 = rotr1((static_cast<uint64_t>(v.y) << 32) | v.x), a1 = rotr1((static_cast<uint64_t>(v.w) << 32) | v.z);
-                    if constexpr (Vec16) ptx::stg_stream_v4(data + origin + e, uint4{static_cast<uint32_t>(a0), static_cast<uint32_t>(a0 >> 32), static_cast<uint32_t>(a1), static_cast<uint32_t>(a1 >> 32)});
-                    else { data[origin + e] = a0; data[origin + e + 1] = a1; }
-                }
-            }
-        } else if constexpr (Dims == 2) {
-            // ---- y direction: 32 two-element column strips x four 16-row segments = 128 threads, scanned
-            //      in registers; final values go straight to global memory (no tile write-back)
-            store_run(tile, tid, r);
-            __syncthreads();
-            const int xq = tid & 31, seg = tid >> 5;
-            const strip_addr_y2<Bits> col(seg, xq);
-            S q[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) q[k] = S::load(tile + col.at(k));
-#pragma unroll
-            for (int k = 1; k < 16; ++k) q[k] = q[k] + q[k - 1];
-            aux.segment_total[seg][2 * xq] = q[15].v[0];
-            aux.segment_total[seg][2 * xq + 1] = q[15].v[1];
-            __syncthreads();
-            S carry{{0, 0}};
-            for (int sg = 0; sg < seg; ++sg) carry = carry + S{{aux.segment_total[sg][2 * xq], aux.segment_total[sg][2 * xq + 1]}};
-            if constexpr (Tma) {
-                // final values back into the tile, in place (every thread rewrites exactly the strips it read)
-#pragma unroll
-                for (int k = 0; k < 16; ++k) (q[k] + carry).rotated_back().store(tile + col.at(k));
-                ptx::fence_proxy_async_smem();
-            } else {
-                char *dst = reinterpret_cast<char *>(data + origin + static_cast<uint64_t>(seg * 16) * a.geom.n[2] + xq * 2);
-                const uint64_t row_bytes = static_cast<uint64_t>(a.geom.n[2]) * sizeof(Bits);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    (q[k] + carry).template emit<Vec16>(reinterpret_cast<Bits *>(dst));
-                    dst += row_bytes;
-                }
-            }
-        } else {
-            // ---- y direction in the tile, z direction fused with rotate + store; 16 x 8 strips per pass -
-            store_run3(tile, tid, r);
-            __syncthreads();
-            const int xq = tid & 7, o = tid >> 3;  // o = z in the y pass, y in the z pass
-            {
-                const strip_addr_y3<Bits> col(o, xq);
-                S q[16];
-#pragma unroll
-                for (int y = 0; y < 16; ++y) q[y] = S::load(tile + col.at(y));
-#pragma unroll
-                for (int y = 1; y < 16; ++y) {
-                    q[y] = q[y] + q[y - 1];
-                    q[y].store(tile + col.at(y));
-                }
-            }
-            __syncthreads();
-            {
-                const strip_addr_z3<Bits> col(o, xq);
-                S q[16];
-#pragma unroll
-                for (int z = 0; z < 16; ++z) q[z] = S::load(tile + col.at(z));
-                if constexpr (Tma) {
-#pragma unroll
-                    for (int z = 1; z < 16; ++z) q[z] = q[z] + q[z - 1];
-                    if constexpr (sizeof(Bits) == 8) {
-                        // double: the value tile already has the layout of the tensor map ([y parity][z][y / 2][x], SWIZZLE_128B):
-                        // in place, every thread rewrites the strips it read
-#pragma unroll
-                        for (int z = 0; z < 16; ++z) q[z].rotated_back().store(tile + col.at(z));
-                    } else {
-                        // float: the passes use a layout with the z parity in the swizzle (tile3_unit), which no tensor map can
-                        // describe; the finished values are re-laid out as plain [z][y][x] rows of 64 bytes under SWIZZLE_64B
-                        // once everybody has read its column
-                        __syncthreads();
-                        uint32_t *out = tile + o * 16 + (((xq >> 1) ^ ((o >> 1) & 3)) << 2) + ((xq & 1) << 1);
-#pragma unroll
-                        for (int z = 0; z < 16; ++z) q[z].rotated_back().store(out + z * 256);
-                    }
-                    ptx::fence_proxy_async_smem();
-                } else {
-                // one byte pointer advanced by the plane pitch (a 64-bit add per store) instead of an element index
-                // that is multiplied out and scaled for every store (IMAD.WIDE + LEA + LEA.HI.X)
-                const uint64_t plane_bytes = static_cast<uint64_t>(a.geom.n[1]) * a.geom.n[2] * sizeof(Bits);
-                char *dst = reinterpret_cast<char *>(data + origin + static_cast<uint64_t>(o) * a.geom.n[2] + xq * 2);
-                q[0].template emit<Vec16>(reinterpret_cast<Bits *>(dst));
-#pragma unroll
-                for (int z = 1; z < 16; ++z) {
-                    q[z] = q[z] + q[z - 1];
-                    dst += plane_bytes;
-                    q[z].template emit<Vec16>(reinterpret_cast<Bits *>(dst));
-                }
-                }
-            }
-        }
+        });
         __syncthreads();  // tile is reused by the cube after next; segment totals by the next cube
         if constexpr (Tma) {
             if (tid == 0) issue_tma_store<Bits, Dims>(tile, &out_map, a.geom, hc);  // everybody's writes + proxy fences are behind the barrier
@@ -1444,6 +1462,152 @@ __global__ void __launch_bounds__(kCubeThreads, sizeof(Bits) == 4 ? 6 : 3) decom
     }
     if constexpr (Tma) {
         if (tid == 0) ptx::tma_store_wait_all();  // shared memory must outlive the stores that read it
+    }
+}
+
+// =====================================================================================================
+// decompress, warp-specialised (float profiles with a TMA-addressable output)
+// =====================================================================================================
+//
+// decompress_kernel keeps two private buffers per 4-warp CTA, so shared memory (6 x 2 x 17 KiB) caps an SM at 24 decoding
+// warps although the tensor-store variants need only 56-64 registers. Here ONE persistent CTA per SM pools the same
+// memory as a ring of S slots: a loader warp streams compressed cubes in (one cp.async.bulk each) as far ahead as slots
+// are free, G decode groups of 4 warps (group g takes the CTA's cubes g, g + G, ...) decode in place and hand the
+// finished tile to a TMA tensor store; a slot returns to the loader once that store has read it. 7 groups = 28 decoding
+// warps per SM from the same 13 slots.
+//   loader          empty[s] -> offsets -> bulk copy (or, for the two kinds of cube a bulk copy must not touch, a
+//                   cooperative copy by the loader warp)                                          -> full[s]
+//   decode group    full[s] -> decode_cube (named barrier of the group) -> tensor store; at the start of its next cube
+//                   the group's first thread waits until the previous store has read its slot     -> empty[s]
+constexpr int kDecodeGroups = 7;  // decompress_ws_kernel: 28 decoding warps + the loader warp = 928 threads, <= 64 registers
+
+template<int S>
+struct dws_aux {
+    uint64_t full[S], empty[S];
+    uint32_t seq[S];      // which of the CTA's cubes the slot holds (mbarrier phase-parity aliasing guard, as in compress_ws_kernel)
+    uint32_t shift[S];    // the image starts `shift` words into the slot (the stream position's misalignment to 16 bytes)
+    uint32_t warp_total[8][4];
+    uint32_t warp_sum[8][4];
+};
+
+template<int Dims, int G>
+__global__ void __launch_bounds__((4 * G + 1) * 32, 1) decompress_ws_kernel(const decompress_launch a, const __grid_constant__ CUtensorMap out_map) {
+    using Bits = uint32_t;
+    using tr = codec_traits<Bits>;
+    constexpr int slot_bytes = decode_plan<Bits>::buffer_bytes;  // 17 KiB: the value tile (16 KiB) + 1 KiB, enough for the longest image
+    constexpr int S = (232448 - 2048) / slot_bytes;
+    constexpr int slot_words = slot_bytes / 4;
+    static_assert(G <= 8 && S > G, "ring too small");
+    static_assert(sizeof(dws_aux<S>) <= 2048, "aux area too small");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint32_t *slots = reinterpret_cast<uint32_t *>(smem_raw);
+    auto &aux = *reinterpret_cast<dws_aux<S> *>(smem_raw + S * slot_bytes);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Bits *stream_cubes = static_cast<const Bits *>(a.stream_cubes);
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            ptx::mbar_init(&aux.full[s], 1);
+            ptx::mbar_init(&aux.empty[s], 1);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();  // the only CTA-wide barrier
+    // this CTA's cubes: t = blockIdx.x + k * gridDim.x, k = 0 .. K-1 (cubes are independent: static round-robin)
+    const uint32_t K = blockIdx.x < a.count ? (a.count - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+
+    if (warp == 4 * G) {
+        // --------------------------------------------------------------------------------------- loader
+        const bool first_cube_unsafe = a.hc_begin == 0
+                && (reinterpret_cast<uintptr_t>(stream_cubes) & ~static_cast<uintptr_t>(15)) < reinterpret_cast<uintptr_t>(a.offsets);
+        // offsets of cube k: even lanes `begin`, odd lanes `end` (a lane-dependent address keeps the value out of the uniform
+        // registers until it is used, see decompress_kernel), fetched one cube ahead
+        auto offsets_of = [&](uint32_t k) -> uint32_t {
+            uint32_t v = 0;
+            if (k < K) {
+                const uint32_t hc = a.hc_begin + blockIdx.x + k * gridDim.x;
+                const uint32_t odd = lane & 1;
+                if (odd || hc) v = __ldg(a.offsets + hc - 1 + odd);  // reference src/ndzip/common.hh:350-358
+            }
+            return v;
+        };
+        uint32_t cur = offsets_of(0);
+        int s = 0;
+        uint32_t parity = 1;  // parity of the phase of empty[s] that ends the previous round (none in round 0)
+        bool first_round = true;
+        for (uint32_t k = 0; k < K; ++k) {
+            const uint32_t next = offsets_of(k + 1);
+            const uint32_t begin = __shfl_sync(kFullMask, cur, 0), end = __shfl_sync(kFullMask, cur, 1);
+            cur = next;
+            if (!first_round) {
+                if (lane == 0) ptx::mbar_wait(&aux.empty[s], parity);
+                __syncwarp();
+            }
+            const uint32_t t = blockIdx.x + k * gridDim.x;
+            uint32_t len = end - begin;
+            if (len > static_cast<uint32_t>(tr::max_cube_words)) len = tr::max_cube_words;  // corrupt header: stay inside the slot
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(stream_cubes + begin);
+            const uint32_t shift = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) >> 2) & 3u;
+            uint32_t *slot = slots + s * slot_words;
+            // the bulk copy moves whole 16-byte blocks: it must not run past the end of the stream (last cube of the range)
+            // nor start in front of the caller's buffer (first cube behind a very short header)
+            const bool bulk = t + 1 < a.count && !(first_cube_unsafe && t == 0);
+            if (bulk) {
+                if (lane == 0) {
+                    aux.seq[s] = k;
+                    aux.shift[s] = shift;
+                    const uint32_t bytes = ((shift + len) * 4u + 15u) & ~15u;
+                    ptx::mbar_arrive_expect_tx(&aux.full[s], bytes);
+                    ptx::bulk_load(slot, src - shift, bytes, &aux.full[s]);
+                }
+            } else {
+                for (uint32_t w = lane; w < len; w += 32) slot[shift + w] = __ldg(src + w);
+                __syncwarp();
+                if (lane == 0) {
+                    aux.seq[s] = k;
+                    aux.shift[s] = shift;
+                    ptx::mbar_arrive(&aux.full[s]);  // (release: the lanes' stores above are ordered before it by __syncwarp)
+                }
+            }
+            if (++s == S) {
+                s = 0;
+                parity ^= 1u;
+                first_round = false;
+            }
+        }
+    } else {
+        // --------------------------------------------------------------------------------------- decode group
+        const int g = warp >> 2, u = tid & (kCubeThreads - 1);
+        int prev_slot = -1;
+        auto release_previous = [&] {
+            // the group's first thread issued the previous cube's tensor store: once the store has read the tile, the slot is free
+            if (u == 0 && prev_slot >= 0) {
+                ptx::tma_store_wait_read();
+                ptx::mbar_arrive(&aux.empty[prev_slot]);
+                prev_slot = -1;
+            }
+        };
+        for (uint32_t k = g; k < K; k += G) {
+            const int s = static_cast<int>(k % static_cast<uint32_t>(S));
+            const uint32_t parity = (k / static_cast<uint32_t>(S)) & 1u;
+            do {  // parity wait + sequence tag, see compress_ws_kernel
+                ptx::mbar_wait(&aux.full[s], parity);
+            } while (*reinterpret_cast<volatile uint32_t *>(&aux.seq[s]) != k);
+            uint32_t *tile = slots + s * slot_words;
+            const uint32_t *image = tile + aux.shift[s];
+            const uint32_t hc = a.hc_begin + blockIdx.x + k * gridDim.x;
+            // 2-D: the four segments' column totals live in the slot's last KiB (the image is dead by the time they are written)
+            auto segment_total = reinterpret_cast<Bits(*)[64]>(tile + 4096);
+            decode_cube<Bits, Dims, store_path::tma>(tile, image, aux.warp_total[g], aux.warp_sum[g], segment_total, a, hc, u,
+                    [&] { ptx::named_barrier(1 + g, kCubeThreads); }, release_previous);
+            ptx::named_barrier(1 + g, kCubeThreads);  // everybody's tile writes and proxy fences are behind this barrier
+            if (u == 0) {
+                issue_tma_store<Bits, Dims>(tile, &out_map, a.geom, hc);
+                prev_slot = s;
+            }
+        }
+        release_previous();
+        if (u == 0) ptx::tma_store_wait_all();  // shared memory must outlive the stores that read it
     }
 }
 
@@ -1700,6 +1864,11 @@ cudaError_t configure_kernels(kernel_config &cfg) {
                         static_cast<int>(compress_ws_smem(dtype)));
                 if (err != cudaSuccess) return err;
             }
+            if (decompress_ws_available(dtype, dims)) {
+                err = dims == 2 ? cudaFuncSetAttribute(decompress_ws_kernel<2, kDecodeGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)
+                                : cudaFuncSetAttribute(decompress_ws_kernel<3, kDecodeGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+                if (err != cudaSuccess) return err;
+            }
             for (int v = 0; v < 3; ++v) {
                 auto fn = decompress_entry(dtype, dims, v);
                 err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(decompress_smem(dtype)));
@@ -1727,6 +1896,16 @@ cudaError_t launch_compress_ws(int dtype, int dims, int variant, const compress_
     const ws_variant v = dtype == 0 ? kWsVariants32[variant] : kWsVariants64[variant];
     const uint32_t threads = static_cast<uint32_t>(4 * v.groups + 1 + v.retire + v.copiers) * 32u;
     compress_ws_entry(dtype, dims, variant)<<<grid, threads, compress_ws_smem(dtype), stream>>>(args, in_map);
+    return cudaGetLastError();
+}
+
+bool decompress_ws_available(int dtype, int dims) { return dtype == 0 && dims >= 2; }  // (1-D float needs 80 registers: 6 CTAs of decompress_kernel)
+
+cudaError_t launch_decompress_ws(int dims, const decompress_launch &args, const CUtensorMap &out_map, uint32_t grid, cudaStream_t stream) {
+    constexpr uint32_t threads = (4 * kDecodeGroups + 1) * 32;
+    constexpr size_t smem = 232448;
+    if (dims == 2) decompress_ws_kernel<2, kDecodeGroups><<<grid, threads, smem, stream>>>(args, out_map);
+    else decompress_ws_kernel<3, kDecodeGroups><<<grid, threads, smem, stream>>>(args, out_map);
     return cudaGetLastError();
 }
 

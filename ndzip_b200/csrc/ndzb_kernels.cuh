@@ -83,6 +83,11 @@ cudaError_t launch_compress_ws(int dtype, int dims, int variant, const compress_
 cudaError_t launch_decompress(int dtype, int dims, int store, const decompress_launch &args, const CUtensorMap *out_map, uint32_t grid,
         cudaStream_t stream);
 
+// Warp-specialised decoder (one persistent CTA per SM, ring of slots, 7 decode groups + loader): float 2-D / 3-D with a
+// TMA-addressable output. grid <= number of SMs.
+bool decompress_ws_available(int dtype, int dims);
+cudaError_t launch_decompress_ws(int dims, const decompress_launch &args, const CUtensorMap &out_map, uint32_t grid, cudaStream_t stream);
+
 // Border: stream_border[i] = bits(data[border_linear_index(i)]) and the inverse.
 // `total_words` (nullable) is a device scalar added to border_base (the compressed words, only known on device).
 cudaError_t launch_pack_border(int dtype, const void *data, const border_geom &bg, void *stream_words,

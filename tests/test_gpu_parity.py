@@ -730,3 +730,19 @@ def test_decoder_output_paths_on_tma_compatible_shapes(nz, oracle, dtype, dims, 
     with load_path(store):
         back = gpu_decompress(stream, dtype, shape)
     assert back.tobytes() == data.tobytes()
+
+
+@pytest.mark.parametrize("decoder", ["ws", "v1"])
+@pytest.mark.parametrize("gen", ["hashed", "smooth", "zeros"])
+@pytest.mark.parametrize("dims", [2, 3])
+def test_both_float_decoders_with_tensor_store(nz, oracle, dims, gen, decoder, monkeypatch):
+    # float 2-D / 3-D with a TMA-addressable output: decompress_ws_kernel (persistent CTA, loader warp + 7 decode groups over
+    # a slot ring; default) and decompress_kernel (NDZB_DECOMPRESS_KERNEL=v1) must both reproduce the data from the ORACLE's
+    # stream; many cubes per CTA, a border, and a stream whose cubes end at every alignment
+    from gpu_util import gpu_decompress
+    monkeypatch.setenv("NDZB_DECOMPRESS_KERNEL", decoder)
+    shape = {2: (64 * 37 + 12, 64 * 9 + 4), 3: (16 * 11 + 4, 16 * 13, 16 * 9 + 8)}[dims]
+    data = np.zeros(shape, "float32") if gen == "zeros" else synth.make(gen, shape, "float32", seed=31)
+    stream = oracle.compress(data)
+    back = gpu_decompress(stream, "float32", shape)
+    assert back.tobytes() == data.tobytes()
