@@ -266,7 +266,7 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
         if (e != cudaSuccess) return cuda_fail(e, "compress_ws_kernel launch");
         if (a.block_desc) ctx->blocks_cur ^= 1;
         ctx->total_cur = total_next;
-        ctx->ticket_base += count + compress_ws_ticket_overdraw(ctx->dtype, ctx->ws_variant, grid);  // wraps together with the device counter
+        ctx->ticket_base += count + compress_ws_ticket_overdraw(ctx->dtype, ctx->dims, ctx->ws_variant, grid, count);  // wraps together with the device counter
         if (ctx->d_stats) {
             unsigned long long h[16];
             NDZB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -834,6 +834,8 @@ __global__ void __launch_bounds__((4 * G + 1 + R + CP) * 32, 1)
         }
     } else if (warp == 4 * G) {
         // ----------------------------------------------------------------------------------- loader
+        constexpr bool Pairs = LA == -2;     // look-ahead 2, drawn as one pair of consecutive tickets
+        constexpr int kLA = Pairs ? 2 : LA;
         if (lane != 0) {
             // The loader warp's other 31 lanes have one job: zero the block words of the NEXT launch (the two arrays
             // alternate), which saves a memset node in front of every launch.
@@ -850,13 +852,13 @@ __global__ void __launch_bounds__((4 * G + 1 + R + CP) * 32, 1)
         // for the slot of the CTA's cube S places back, whose retirement needs lengths of earlier cubes).
         // (LA == 0: the ticket is drawn only when the slot is free, right before the load is issued, and the loader waits
         // for the atomic: no SM ever holds a ticket it cannot load yet.)
-        constexpr int kTk = LA > 0 ? LA : 1;
+        constexpr int kTk = kLA > 0 ? kLA : 1;
         uint32_t tk[kTk];
         bool ended = false;  // LA == 0: an out-of-range ticket has been drawn, no more draws
-        if constexpr (LA > 0) {
-            const uint32_t first = atomicAdd(a.ticket, static_cast<uint32_t>(LA)) - a.ticket_base;
+        if constexpr (kLA > 0) {
+            const uint32_t first = atomicAdd(a.ticket, static_cast<uint32_t>(kLA)) - a.ticket_base;
 #pragma unroll
-            for (int j = 0; j < LA; ++j) tk[j] = first + j;
+            for (int j = 0; j < kLA; ++j) tk[j] = first + j;
         }
         int s = 0;
         uint32_t parity = 1;  // parity of the phase of empty[s] that ends the PREVIOUS round (none in round 0)
@@ -872,7 +874,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R + CP) * 32, 1)
                 const long long c1 = now();
                 st_a += c1 - c0;
                 st_b += now() - c1;
-                if constexpr (LA == 0) {
+                if constexpr (kLA == 0) {
                     if (!ended) tk[0] = atomicAdd(a.ticket, 1u) - a.ticket_base;
                     ended = tk[0] >= a.count;
                 }
@@ -892,8 +894,19 @@ __global__ void __launch_bounds__((4 * G + 1 + R + CP) * 32, 1)
                     // The next ticket is drawn AFTER the load is on its way: the proxy fence above is a MEMBAR, which
                     // waits for every memory operation this thread has in flight — with the atomic in front of it the
                     // loader stood still for an L2 round trip per cube (slot free -> load issued: 2300 cycles).
-                    if constexpr (LA > 0) tk[j] = atomicAdd(a.ticket, 1u) - a.ticket_base;
+                    if constexpr (Pairs) {
+                        // tickets are drawn two at a time: consecutive cubes (x neighbours: the two halves of the same 128-byte
+                        // lines of a 3-D float grid) are loaded back to back by the same SM
+                        if (j == 1) {
+                            const uint32_t first = atomicAdd(a.ticket, 2u) - a.ticket_base;
+                            tk[0] = first;
+                            tk[1] = first + 1;
+                        }
+                    } else if constexpr (kLA > 0) {
+                        tk[j] = atomicAdd(a.ticket, 1u) - a.ticket_base;
+                    }
                 } else {
+                    if constexpr (Pairs) tk[0] = tk[1] = t;  // out of range: nothing more to load, no more draws
                     aux.ticket[s] = kNoTicket - poison;  // end marker number `poison`
                     aux.seq[s] = seq;
                     ptx::mbar_arrive(&aux.full[s]);
@@ -1751,7 +1764,7 @@ using compress_ws_fn = void (*)(const compress_launch, const CUtensorMap);
 struct ws_variant {
     int groups, retire;
     int look_back_depth;  // windows of 32 * depth cubes per round trip (negative: read with ld.global.cg)
-    int ticket_lookahead;
+    int ticket_lookahead;  // tickets a loader holds ahead of its loads; -2: two, drawn as a pair of consecutive cubes
     int copiers;  // copy warps: 0 = the retire warps copy their cubes out themselves
     int early;  // look-back started when the cube's length is known (1) / when its image is complete (0) / 1 for 3-D profiles only (2)
     bool dynamic;  // encoder groups take the CTA's next cube when they become free (instead of cube g, g+G, ...)
@@ -1773,7 +1786,10 @@ constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 2,
 #ifndef NDZB_LA
 #define NDZB_LA 1
 #endif
-constexpr ws_variant kWsVariants32[] = {{5, 4, 0, NDZB_LA, 0, 1, false, false}};
+#ifndef NDZB_LA32
+#define NDZB_LA32 -2  // float: pairs of consecutive tickets for 3-D (falls back to 1 for 1-D / 2-D)
+#endif
+constexpr ws_variant kWsVariants32[] = {{5, 4, 0, NDZB_LA32, 0, 1, false, false}};
 constexpr ws_variant kWsVariants64[] = {{3, 2, 1, NDZB_LA, 0, 1, false, false}};
 #endif
 constexpr int kNumWsVariants32 = sizeof(kWsVariants32) / sizeof(ws_variant);
@@ -1783,7 +1799,8 @@ template<typename Bits, int Dims, int V>
 compress_ws_fn compress_ws_variant_fn() {
     if constexpr (sizeof(Bits) == 4) {
         constexpr ws_variant v = kWsVariants32[V];
-        return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, v.ticket_lookahead, v.copiers,
+        // pairs of consecutive tickets pay for 3-D float only (64-byte rows: x neighbours share 128-byte lines), cf. ws_lookahead()
+        return compress_ws_kernel<Bits, Dims, v.groups, v.retire, v.look_back_depth, (v.ticket_lookahead == -2 && Dims != 3) ? 1 : v.ticket_lookahead, v.copiers,
                 v.early == 1 || (v.early == 2 && Dims == 3), v.dynamic, v.stats>;
     } else {
         constexpr ws_variant v = kWsVariants64[V];
@@ -1830,10 +1847,18 @@ uint32_t compress_ticket_overdraw(uint32_t grid) {
     return grid;  // every CTA draws one ticket up front and one more per cube it processes
 }
 int compress_ws_variants(int dtype);
-uint32_t compress_ws_ticket_overdraw(int dtype, int variant, uint32_t grid) {
+// effective ticket look-ahead of (dtype, dims, variant): -2 = pairs (see compress_ws_variant_fn)
+static int ws_lookahead(int dtype, int dims, int variant) {
     if (variant < 0 || variant >= compress_ws_variants(dtype)) variant = 0;
-    const ws_variant v = dtype == 0 ? kWsVariants32[variant] : kWsVariants64[variant];
-    return grid * static_cast<uint32_t>(v.ticket_lookahead > 0 ? v.ticket_lookahead : 1);  // drawn beyond `count`: the look-ahead, or the one ticket that ends a late-binding loader
+    const int la = (dtype == 0 ? kWsVariants32[variant] : kWsVariants64[variant]).ticket_lookahead;
+    return la == -2 && !(dtype == 0 && dims == 3) ? 1 : la;
+}
+// Tickets a launch draws beyond `count` (the host mirrors the device's free-running ticket counter).
+uint32_t compress_ws_ticket_overdraw(int dtype, int dims, int variant, uint32_t grid, uint32_t count) {
+    const int la = ws_lookahead(dtype, dims, variant);
+    // pairs: every loader draws one pair up front and one more per fully valid pair it loads: 2 * grid + 2 * floor(count / 2) in all
+    if (la == -2) return 2u * grid - (count & 1u);
+    return grid * static_cast<uint32_t>(la > 0 ? la : 1);  // the look-ahead, or the one ticket that ends a late-binding loader
 }
 int compress_ws_variants(int dtype) { return dtype == 0 ? kNumWsVariants32 : kNumWsVariants64; }
 bool tuning_build() { return kTuning; }

@@ -73,7 +73,7 @@ uint32_t compress_ticket_overdraw(uint32_t grid);
 cudaError_t launch_compress(int dtype, int dims, load_path path, const compress_launch &args, const CUtensorMap *tmap,
         uint32_t grid, cudaStream_t stream);
 // Warp-specialised compress kernel (TMA-compatible inputs only): one CTA per SM, `variant` < compress_ws_variants(dtype).
-uint32_t compress_ws_ticket_overdraw(int dtype, int variant, uint32_t grid);
+uint32_t compress_ws_ticket_overdraw(int dtype, int dims, int variant, uint32_t grid, uint32_t count);
 int compress_ws_variants(int dtype);
 bool tuning_build();  // compiled with -DNDZB_TUNING (variants 1-4, statistics, debug aids, compress_kernel for TMA inputs)
 bool compress_ws_uses_blocks(int dtype, int variant);  // two-level look-back: needs block_desc / block_desc_next

@@ -746,3 +746,23 @@ def test_both_float_decoders_with_tensor_store(nz, oracle, dims, gen, decoder, m
     stream = oracle.compress(data)
     back = gpu_decompress(stream, "float32", shape)
     assert back.tobytes() == data.tobytes()
+
+
+def test_paired_tickets_keep_the_context_in_step(nz, oracle):
+    # 3-D float loaders draw tickets in pairs; the host mirrors the device's free-running ticket counter (2 * grid - (count & 1)
+    # tickets beyond `count` per launch). Odd and even cube counts, one cube, more cubes than SMs, back to back on ONE context:
+    # a miscounted launch would leave the next one waiting for tickets that were never drawn (or skipping cubes).
+    import torch
+    from gpu_util import to_device
+    shapes = [(48, 48, 48), (16, 16, 16), (16, 16, 80), (32, 48, 64), (16, 16, 16), (112, 48, 48), (48, 48, 48)]
+    comp = nz.make_cuda_compressor("float32", nz.compressor_requirements(shapes))
+    for i, shape in enumerate(shapes + shapes):
+        data = synth.make("smooth" if i % 2 else "hashed", shape, "float32", seed=40 + i)
+        expect = oracle.compress(data)
+        d_stream = torch.zeros(nz.compressed_length_bound("float32", shape), dtype=torch.int32, device="cuda")
+        d_len = torch.zeros(1, dtype=torch.int32, device="cuda")
+        comp.compress(to_device(data), shape, d_stream, d_len)
+        torch.cuda.synchronize()
+        n = int(d_len.cpu().numpy().view(np.uint32)[0])
+        assert n == expect.size, (shape, n, expect.size)
+        assert np.array_equal(d_stream[:n].cpu().numpy().view(np.uint32), expect), shape
