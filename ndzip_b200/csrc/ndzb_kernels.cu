@@ -1508,7 +1508,7 @@ struct dws_aux {
 
 // Cubes are dealt to the CTAs in runs of consecutive cubes. 3-D float: pairs — x neighbours, i.e. the two 64-byte halves of the
 // same 128-byte lines, are then written back to back by one SM (cfg2 decompress 0.1737 -> 0.1671 ms; runs of four: 0.1776).
-template<int Dims> constexpr uint32_t decode_run() { return Dims == 3 ? 2u : 1u; }
+template<int Dims> struct decode_run { static constexpr uint32_t value = Dims == 3 ? 2u : 1u; };
 
 template<int Dims, int G>
 __global__ void __launch_bounds__((4 * G + 1) * 32, 1) decompress_ws_kernel(const decompress_launch a, const __grid_constant__ CUtensorMap out_map) {
@@ -1533,7 +1533,7 @@ __global__ void __launch_bounds__((4 * G + 1) * 32, 1) decompress_ws_kernel(cons
         ptx::fence_mbar_init();
     }
     __syncthreads();  // the only CTA-wide barrier
-    constexpr uint32_t kDecRun = decode_run<Dims>();
+    constexpr uint32_t kDecRun = decode_run<Dims>::value;
     // this CTA's cubes (cubes are independent: static round-robin over runs of kDecRun consecutive cubes):
     // k = 0 .. K-1 -> t = kDecRun * (blockIdx.x + (k / kDecRun) * gridDim.x) + k % kDecRun
     auto cube_of = [&](uint32_t k) { return kDecRun * (blockIdx.x + (k / kDecRun) * gridDim.x) + k % kDecRun; };
