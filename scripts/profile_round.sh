@@ -11,7 +11,7 @@ common="--steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-sustained"
 for wl in $wls; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:compress_ws -s 4 -c 1 -f -o gpurun_out/${tag}_${wl}_compress_ws \
       python bench.py --workload $wl $common > gpurun_out/${tag}_${wl}_ncu_c.log 2>&1
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:decompress_kernel -s 4 -c 1 -f -o gpurun_out/${tag}_${wl}_decompress \
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:decompress -s 4 -c 1 -f -o gpurun_out/${tag}_${wl}_decompress \
       python bench.py --workload $wl $common > gpurun_out/${tag}_${wl}_ncu_d.log 2>&1
 done
 [ -z "$bench" ] && exit 0
