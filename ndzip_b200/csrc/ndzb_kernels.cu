@@ -1181,11 +1181,11 @@ __device__ __forceinline__ void issue_tma_store(const uint32_t *tile, const CUte
 template<typename Bits, int Dims, store_path Out, typename Sync, typename Hook>
 __device__ __forceinline__ void decode_cube(uint32_t *tile, const uint32_t *image, uint32_t *warp_total, Bits *warp_sum, Bits (*segment_total)[64],
         const decompress_launch &a, uint32_t hc, int tid, Sync sync, Hook after_first_barrier) {
-    constexpr bool Vec16 = Out != store_path::scalar;
+    [[maybe_unused]] constexpr bool Vec16 = Out != store_path::scalar;
     constexpr bool Tma = Out == store_path::tma;
     using tr = codec_traits<Bits>;
-    const int lane = tid & 31, warp = tid >> 5;
-    Bits *data = static_cast<Bits *>(a.data);
+    [[maybe_unused]] const int lane = tid & 31, warp = tid >> 5;
+    [[maybe_unused]] Bits *data = static_cast<Bits *>(a.data);
     // ---- chunk heads -> where each chunk's planes start ------------------------------------------------
     Bits head;
     uint32_t count;
@@ -1798,9 +1798,9 @@ struct ws_variant {
 constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}, {5, 4, 0, 1, 3, 1, false, false}, {5, 4, 0, 1, 2, 1, false, false},
         {5, 3, 0, 1, 3, 1, false, false}, {5, 4, 0, 1, 0, 1, false, true}, {4, 4, 0, 1, 4, 1, false, false}, {5, 3, 0, 1, 4, 1, false, false},
         {5, 5, 0, 1, 2, 1, false, false}};
-constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 2, 1, 1, 2, 1, false, false}, {3, 2, 1, 1, 1, 1, false, false},
-        {3, 3, 1, 1, 2, 1, false, false}, {3, 2, 1, 1, 0, 1, false, true}, {3, 2, 1, 1, 3, 1, false, false}, {3, 3, 1, 1, 3, 1, false, false},
-        {3, 4, 1, 1, 2, 1, false, false}};
+constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {4, 2, 1, 1, 0, 1, false, false}, {4, 3, 1, 1, 0, 1, false, false},
+        {3, 3, 1, 1, 2, 1, false, false}, {3, 2, 1, 1, 0, 1, false, true}, {3, 2, 1, 1, 3, 1, false, false}, {3, 2, 1, 2, 0, 1, false, false},
+        {4, 2, 0, 1, 0, 1, false, false}};
 #else
 #ifndef NDZB_LA
 #define NDZB_LA 1
