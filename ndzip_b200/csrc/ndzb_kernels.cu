@@ -1181,11 +1181,12 @@ __device__ __forceinline__ void issue_tma_store(const uint32_t *tile, const CUte
 template<typename Bits, int Dims, store_path Out, typename Sync, typename Hook>
 __device__ __forceinline__ void decode_cube(uint32_t *tile, const uint32_t *image, uint32_t *warp_total, Bits *warp_sum, Bits (*segment_total)[64],
         const decompress_launch &a, uint32_t hc, int tid, Sync sync, Hook after_first_barrier) {
-    [[maybe_unused]] constexpr bool Vec16 = Out != store_path::scalar;
+    constexpr bool Vec16 = Out != store_path::scalar;
     constexpr bool Tma = Out == store_path::tma;
     using tr = codec_traits<Bits>;
-    [[maybe_unused]] const int lane = tid & 31, warp = tid >> 5;
-    [[maybe_unused]] Bits *data = static_cast<Bits *>(a.data);
+    const int lane = tid & 31, warp = tid >> 5;
+    Bits *data = static_cast<Bits *>(a.data);
+    (void) Vec16, (void) warp, (void) data;  // not every (profile, output path) instantiation uses all three
     // ---- chunk heads -> where each chunk's planes start ------------------------------------------------
     Bits head;
     uint32_t count;
