@@ -13,6 +13,7 @@ HEADERS = ["ndzb_cube.cuh", "ndzb_ptx.cuh", "ndzb_kernels.cuh"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "-diag-suppress=177",  # "declared but never referenced": locals that only some template instantiations use
 ]
 
 

@@ -1186,7 +1186,6 @@ __device__ __forceinline__ void decode_cube(uint32_t *tile, const uint32_t *imag
     using tr = codec_traits<Bits>;
     const int lane = tid & 31, warp = tid >> 5;
     Bits *data = static_cast<Bits *>(a.data);
-    (void) Vec16, (void) warp, (void) data;  // not every (profile, output path) instantiation uses all three
     // ---- chunk heads -> where each chunk's planes start ------------------------------------------------
     Bits head;
     uint32_t count;
