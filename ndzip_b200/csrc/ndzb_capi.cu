@@ -4,6 +4,8 @@
 #include "../../include/ndzip_b200.h"
 #include "ndzb_kernels.cuh"
 
+#include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -157,7 +159,8 @@ struct ndzb_ctx {
     // pipelined offload: copy-in / copy-out streams, per-chunk events, pinned per-chunk totals
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done, ev_k0, ev_k1;
-    uint32_t *h_totals = nullptr;  // pinned
+    uint32_t *h_totals = nullptr;  // pinned + mapped: the compress kernels store their running totals here themselves
+    uint32_t *d_totals = nullptr;  // device-side address of h_totals
 };
 
 namespace {
@@ -219,7 +222,7 @@ int reset_scan_state(ndzb_ctx *ctx) {
 // Enqueue the compression of cubes [hc_begin, hc_begin + count) (count > 0).
 int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g, uint32_t hc_begin, uint32_t count,
         void *out_cubes, uint32_t *out_offsets, uint32_t *pad_word, uint32_t *length_out, uint32_t length_add,
-        bool chained = false) {
+        bool chained = false, uint32_t *total_host = nullptr) {
     if (int rc = ensure_descriptors(ctx, count)) return rc;
     const load_path path = choose_path(ctx, d_data, g);
     CUtensorMap map{};
@@ -245,6 +248,7 @@ int enqueue_compress_range(ndzb_ctx *ctx, const void *d_data, const grid_geom &g
     a.base_words = chained ? ctx->d_counters + 1 + ctx->total_cur : nullptr;
     const int total_next = ctx->total_cur ^ 1;   // (the host's book-keeping only advances once the launch has succeeded)
     a.total_words = ctx->d_counters + 1 + total_next;
+    a.total_host = total_host;
     a.length_out = length_out;
     a.length_add = length_add;
     a.desc = ctx->d_desc;
@@ -367,7 +371,8 @@ int enqueue_decompress_range(ndzb_ctx *ctx, const void *stream_cubes, const uint
 // and D2H of slab c-1 run on three streams, so the call is bounded by max(H2D, D2H) over PCIe instead of
 // their sum. Used for border-free extents above a size threshold; everything else takes the simple path.
 constexpr int kMaxChunks = 128;
-constexpr size_t kChunkBytes = size_t{32} << 20;
+constexpr size_t kChunkBytes = size_t{32} << 20;            // compression: the tail after the last H2D copy wants small chunks
+constexpr size_t kDecompressChunkBytes = size_t{64} << 20;  // decompression: the D2H copies (the long pole) want few, large copies
 constexpr size_t kPipelineMinBytes = size_t{16} << 20;
 
 size_t pipeline_min_bytes() {
@@ -377,13 +382,16 @@ size_t pipeline_min_bytes() {
 
 struct chunk_plan {
     int chunks = 0;
-    uint32_t rows_per_chunk = 0;   // cube rows (along dimension 0) per chunk
+    std::vector<uint32_t> row_begin;  // chunk c = cube rows [row_begin[c], row_begin[c + 1]) along dimension 0
     uint32_t cube_rows = 0;
     uint32_t cubes_per_row = 0;
     uint64_t elems_per_cube_row = 0;
 };
 
-chunk_plan plan_chunks(int dims, const uint32_t *size, const grid_geom &g, size_t elem_bytes) {
+// `small_first`: the chunks at the FRONT are single cube rows (decompression: the D2H copies are the long pole and
+// cannot start before the first chunk has been uploaded and decoded); otherwise the chunks at the BACK are
+// (compression: after the last H2D copy only that chunk's kernel and its D2H copy remain).
+chunk_plan plan_chunks(int dims, const uint32_t *size, const grid_geom &g, size_t elem_bytes, bool small_first) {
     chunk_plan p;
     p.cube_rows = size[0] / side_for(dims);
     if (p.cube_rows == 0) return p;
@@ -391,24 +399,45 @@ chunk_plan plan_chunks(int dims, const uint32_t *size, const grid_geom &g, size_
     p.elems_per_cube_row = static_cast<uint64_t>(side_for(dims));
     for (int d = 1; d < dims; ++d) p.elems_per_cube_row *= size[d];
     const uint64_t row_bytes = p.elems_per_cube_row * elem_bytes;
-    uint64_t chunk_bytes = kChunkBytes;
+    uint64_t chunk_bytes = small_first ? kDecompressChunkBytes : kChunkBytes;
     if (const char *env = getenv("NDZB_CHUNK_BYTES")) chunk_bytes = strtoull(env, nullptr, 10);  // tests / tuning
     uint64_t rows = chunk_bytes / (row_bytes ? row_bytes : 1);
     if (rows == 0) rows = 1;
     uint64_t chunks = (p.cube_rows + rows - 1) / rows;
-    if (chunks > kMaxChunks) {
-        rows = (p.cube_rows + kMaxChunks - 1) / kMaxChunks;
+    if (chunks > kMaxChunks - 4) {
+        rows = (p.cube_rows + (kMaxChunks - 4) - 1) / (kMaxChunks - 4);
         chunks = (p.cube_rows + rows - 1) / rows;
     }
-    p.rows_per_chunk = static_cast<uint32_t>(rows);
-    p.chunks = static_cast<int>(chunks);
+    // ramp: one nominal chunk at the small end is cut into (at most 4) pieces of rows/4
+    std::vector<uint32_t> lens;
+    uint64_t left = p.cube_rows;
+    const uint64_t piece = (rows + 3) / 4;
+    uint64_t ramp = rows > 1 && chunks > 1 ? rows : 0;
+    while (ramp > 0 && left > 0) {
+        const uint64_t n = ramp < piece ? ramp : piece;
+        lens.push_back(static_cast<uint32_t>(n < left ? n : left));
+        left -= lens.back();
+        ramp -= n;
+    }
+    while (left > 0) {
+        lens.push_back(static_cast<uint32_t>(rows < left ? rows : left));
+        left -= lens.back();
+    }
+    // built small-first; a remainder chunk (cube_rows not a multiple of `rows`) ends up at the back either way
+    if (!small_first) std::reverse(lens.begin(), lens.end());
+    p.row_begin.push_back(0);
+    for (uint32_t n : lens) p.row_begin.push_back(p.row_begin.back() + n);
+    p.chunks = static_cast<int>(lens.size());
     return p;
 }
 
 int ensure_pipeline(ndzb_ctx *ctx, int chunks) {
     if (!ctx->s_in) NDZB_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     if (!ctx->s_out) NDZB_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
-    if (!ctx->h_totals) NDZB_CUDA(cudaHostAlloc(&ctx->h_totals, kMaxChunks * sizeof(uint32_t), cudaHostAllocDefault));
+    if (!ctx->h_totals) {
+        NDZB_CUDA(cudaHostAlloc(&ctx->h_totals, kMaxChunks * sizeof(uint32_t), cudaHostAllocMapped));
+        NDZB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&ctx->d_totals), ctx->h_totals, 0));
+    }
     while (static_cast<int>(ctx->ev_in.size()) < chunks) {
         cudaEvent_t a, b, c, d;
         NDZB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -435,6 +464,53 @@ int sum_kernel_time(ndzb_ctx *ctx, int chunks, uint64_t *kernel_ns) {
     return NDZB_OK;
 }
 
+// NDZB_PIPE_TRACE=1: timeline of one pipelined call on stderr (ms since the call's first enqueue): per chunk the end
+// of its H2D copy, start / end of its kernel, end of its D2H copy, and the host clock at every synchronisation.
+struct pipe_trace {
+    bool on = false;
+    cudaEvent_t t0 = nullptr;
+    std::vector<cudaEvent_t> in, out;
+    std::vector<double> host_sync;
+    std::chrono::steady_clock::time_point h0;
+    explicit pipe_trace(int chunks) {
+        const char *e = getenv("NDZB_PIPE_TRACE");
+        on = e && atoi(e) != 0;
+        if (!on) return;
+        cudaEventCreate(&t0);
+        in.resize(chunks);
+        out.resize(chunks, nullptr);
+        for (auto &x : in) cudaEventCreate(&x);
+        h0 = std::chrono::steady_clock::now();
+    }
+    double host_ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count(); }
+    void begin(cudaStream_t s) { if (on) cudaEventRecord(t0, s); }
+    void mark_in(int c, cudaStream_t s) { if (on) cudaEventRecord(in[c], s); }
+    void mark_out(int c, cudaStream_t s) {
+        if (!on) return;
+        if (!out[c]) cudaEventCreate(&out[c]);
+        cudaEventRecord(out[c], s);
+    }
+    void mark_host() { if (on) host_sync.push_back(host_ms()); }
+    void report(const char *what, const std::vector<cudaEvent_t> &k0, const std::vector<cudaEvent_t> &k1) {
+        if (!on) return;
+        const double end = host_ms();
+        fprintf(stderr, "pipe trace %s: %zu chunks, host total %.3f ms, host syncs at", what, in.size(), end);
+        for (double h : host_sync) fprintf(stderr, " %.3f", h);
+        fprintf(stderr, "\n  chunk: h2d_end k_begin k_end d2h_end (ms since first enqueue on the copy-in stream)\n");
+        for (size_t c = 0; c < in.size(); ++c) {
+            float a = 0, b = 0, d = 0, e = -1;
+            cudaEventElapsedTime(&a, t0, in[c]);
+            cudaEventElapsedTime(&b, t0, k0[c]);
+            cudaEventElapsedTime(&d, t0, k1[c]);
+            if (out[c]) cudaEventElapsedTime(&e, t0, out[c]);
+            fprintf(stderr, "  %3zu: %8.3f %8.3f %8.3f %8.3f\n", c, a, b, d, e);
+        }
+        cudaEventDestroy(t0);
+        for (auto x : in) cudaEventDestroy(x);
+        for (auto x : out) if (x) cudaEventDestroy(x);
+    }
+};
+
 int pipelined_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uint32_t *size, void *h_stream,
         uint32_t *length_words, uint64_t *kernel_ns, const grid_geom &g, const chunk_plan &plan) {
     const size_t wb = word_bytes(ctx->dtype);
@@ -455,43 +531,46 @@ int pipelined_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uint32
     NDZB_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
     NDZB_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->ev_begin, 0));
     NDZB_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_begin, 0));
+    pipe_trace trace(plan.chunks);
+    trace.begin(ctx->s_in);
 
     for (int c = 0; c < plan.chunks; ++c) {
-        const uint32_t row0 = c * plan.rows_per_chunk;
-        const uint32_t row1 = (c + 1 == plan.chunks) ? plan.cube_rows : row0 + plan.rows_per_chunk;
+        const uint32_t row0 = plan.row_begin[c], row1 = plan.row_begin[c + 1];
         const uint64_t e0 = row0 * plan.elems_per_cube_row;
         const uint64_t e1 = (c + 1 == plan.chunks) ? n_elems : row1 * plan.elems_per_cube_row;
         NDZB_CUDA(cudaMemcpyAsync(d_in + e0 * wb, h_in + e0 * wb, (e1 - e0) * wb, cudaMemcpyHostToDevice, ctx->s_in));
+        trace.mark_in(c, ctx->s_in);
         NDZB_CUDA(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
         NDZB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0));
         NDZB_CUDA(cudaEventRecord(ctx->ev_k0[c], ctx->stream));
         const uint32_t hb = row0 * plan.cubes_per_row, he = row1 * plan.cubes_per_row;
         if (int rc = enqueue_compress_range(ctx, ctx->d_in, g, hb, he - hb, cubes, offsets + hb, c == 0 ? pad : nullptr,
-                    c + 1 == plan.chunks ? ctx->d_length : nullptr, hdr, c != 0)) {
+                    c + 1 == plan.chunks ? ctx->d_length : nullptr, hdr, c != 0, ctx->d_totals + c)) {
             return rc;
         }
         NDZB_CUDA(cudaEventRecord(ctx->ev_k1[c], ctx->stream));
-        NDZB_CUDA(cudaMemcpyAsync(ctx->h_totals + c, ctx->d_counters + 1 + ctx->total_cur, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         NDZB_CUDA(cudaEventRecord(ctx->ev_done[c], ctx->stream));
     }
-    // drain: the compressed cubes go back on the copy-out stream as their totals become known on the host. The copy
-    // sizes are only known there, so every D2H needs one host synchronisation: early chunks are sent in batches of
-    // kDrainBatch (their D2H hides under the H2D of later chunks anyway), the last ones one by one so that little is
-    // left to copy when the last kernel ends.
-    constexpr int kDrainBatch = 8, kDrainTail = 4;
+    // drain: the compressed cubes of chunk c go back on the copy-out stream as soon as its kernel has finished. The size
+    // of that copy is only known on the device; the kernel stores its running total straight into mapped host memory
+    // (total_host), so the compute stream holds nothing but kernels. (A 4-byte D2H copy node per chunk in that stream
+    // queued behind the large copies of the copy-out stream on the same copy engine and stalled every later kernel:
+    // profiles/README.md, round 2, "offloader timeline".) One host synchronisation per chunk; the host has nothing else to do.
     uint32_t prev = 0;
     for (int c = 0; c < plan.chunks; ++c) {
-        const bool sync_here = plan.chunks - 1 - c < kDrainTail || (c + 1) % kDrainBatch == 0;
-        if (!sync_here) continue;
         NDZB_CUDA(cudaEventSynchronize(ctx->ev_done[c]));
-        const uint32_t tot = ctx->h_totals[c];
+        trace.mark_host();
+        const uint32_t tot = *static_cast<volatile uint32_t *>(ctx->h_totals + c);
         const size_t off = (static_cast<size_t>(hdr) + prev) * wb;
         if (tot > prev) NDZB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, static_cast<size_t>(tot - prev) * wb, cudaMemcpyDeviceToHost, ctx->s_out));
+        trace.mark_out(c, ctx->s_out);
         prev = tot;
     }
     NDZB_CUDA(cudaMemcpyAsync(h_out, d_out, static_cast<size_t>(hdr) * wb, cudaMemcpyDeviceToHost, ctx->s_out));
     NDZB_CUDA(cudaStreamSynchronize(ctx->s_out));
     NDZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    trace.mark_host();
+    trace.report("compress", ctx->ev_k0, ctx->ev_k1);
     *length_words = hdr + prev;
     return sum_kernel_time(ctx, plan.chunks, kernel_ns);
 }
@@ -512,15 +591,17 @@ int pipelined_decompress(ndzb_ctx *ctx, const void *h_stream, void *h_data, int 
     NDZB_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
     NDZB_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->ev_begin, 0));
     NDZB_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_begin, 0));
+    pipe_trace trace(plan.chunks);
+    trace.begin(ctx->s_in);
     NDZB_CUDA(cudaMemcpyAsync(d_stream, h_in, static_cast<size_t>(hdr) * wb, cudaMemcpyHostToDevice, ctx->s_in));
 
     for (int c = 0; c < plan.chunks; ++c) {
-        const uint32_t row0 = c * plan.rows_per_chunk;
-        const uint32_t row1 = (c + 1 == plan.chunks) ? plan.cube_rows : row0 + plan.rows_per_chunk;
+        const uint32_t row0 = plan.row_begin[c], row1 = plan.row_begin[c + 1];
         const uint32_t hb = row0 * plan.cubes_per_row, he = row1 * plan.cubes_per_row;
         const size_t w0 = static_cast<size_t>(hdr) + (hb ? h_offsets[hb - 1] : 0u);
         const size_t w1 = static_cast<size_t>(hdr) + h_offsets[he - 1];
         NDZB_CUDA(cudaMemcpyAsync(d_stream + w0 * wb, h_in + w0 * wb, (w1 - w0) * wb, cudaMemcpyHostToDevice, ctx->s_in));
+        trace.mark_in(c, ctx->s_in);
         NDZB_CUDA(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
         NDZB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0));
         NDZB_CUDA(cudaEventRecord(ctx->ev_k0[c], ctx->stream));
@@ -534,9 +615,13 @@ int pipelined_decompress(ndzb_ctx *ctx, const void *h_stream, void *h_data, int 
         const uint64_t e0 = row0 * plan.elems_per_cube_row;
         const uint64_t e1 = (c + 1 == plan.chunks) ? n_elems : row1 * plan.elems_per_cube_row;
         NDZB_CUDA(cudaMemcpyAsync(h_out + e0 * wb, d_data + e0 * wb, (e1 - e0) * wb, cudaMemcpyDeviceToHost, ctx->s_out));
+        trace.mark_out(c, ctx->s_out);
     }
+    trace.mark_host();
     NDZB_CUDA(cudaStreamSynchronize(ctx->s_out));
     NDZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    trace.mark_host();
+    trace.report("decompress", ctx->ev_k0, ctx->ev_k1);
     return sum_kernel_time(ctx, plan.chunks, kernel_ns);
 }
 
@@ -803,7 +888,7 @@ int ndzb_offload_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uin
     {
         const grid_geom g = make_geom(dims, size);
         if (g.num_cubes > 0 && make_border(dims, size).count == 0 && in_bytes >= pipeline_min_bytes() && !getenv("NDZB_NO_PIPELINE")) {
-            const chunk_plan plan = plan_chunks(dims, size, g, wb);
+            const chunk_plan plan = plan_chunks(dims, size, g, wb, false);
             if (plan.chunks > 1) {
                 ctx->last_launches = 0;
                 uint64_t ns = 0;
@@ -869,7 +954,7 @@ int ndzb_offload_decompress(ndzb_ctx *ctx, const void *h_stream, uint32_t length
     {
         const grid_geom g = make_geom(dims, size);
         if (g.num_cubes > 0 && make_border(dims, size).count == 0 && out_bytes >= pipeline_min_bytes() && !getenv("NDZB_NO_PIPELINE")) {
-            const chunk_plan plan = plan_chunks(dims, size, g, wb);
+            const chunk_plan plan = plan_chunks(dims, size, g, wb, true);
             if (plan.chunks > 1) {
                 uint64_t ns = 0;
                 const int rc = pipelined_decompress(ctx, h_stream, h_data, dims, size, (kernel_ns || verbose()) ? &ns : nullptr, g, plan);

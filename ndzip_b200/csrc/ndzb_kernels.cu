@@ -529,6 +529,7 @@ __global__ void __launch_bounds__(kCubeThreads)
                 if (prev_t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452
                 if (prev_t == a.count - 1) {
                     *a.total_words = after;
+                    if (a.total_host) *a.total_host = after;
                     if (a.length_out) *a.length_out = a.length_add + after;  // cuda_codec.inl:507-511
                 }
             }
@@ -593,7 +594,12 @@ template<typename Bits>
 struct ws_plan {
     static constexpr int slot_bytes = smem_plan<Bits>::slot_bytes;
     static constexpr int aux_bytes = 2048;
-    static constexpr int slots = (232448 - aux_bytes) / slot_bytes;  // 227 KiB of dynamic shared memory per CTA
+    static constexpr int max_slots = (232448 - aux_bytes) / slot_bytes;  // 227 KiB of dynamic shared memory per CTA
+#if defined(NDZB_WS_SLOTS)  // tuning builds: a shorter ring
+    static constexpr int slots = NDZB_WS_SLOTS < max_slots ? NDZB_WS_SLOTS : max_slots;
+#else
+    static constexpr int slots = max_slots;
+#endif
 };
 
 template<int S, int G>
@@ -984,6 +990,7 @@ __global__ void __launch_bounds__((4 * G + 1 + R + CP) * 32, 1)
                 if (t == 0 && a.pad_word) *a.pad_word = 0;  // cuda_codec.inl:446-452
                 if (t == a.count - 1) {
                     *a.total_words = after;
+                    if (a.total_host) *a.total_host = after;
                     if (a.length_out) *a.length_out = a.length_add + after;  // cuda_codec.inl:507-511
                 }
             }

@@ -35,6 +35,8 @@ struct compress_launch {
     uint32_t *pad_word;        // nullable: header padding word to be zeroed (f64, odd H)
     const uint32_t *base_words; // nullable: device scalar added to every offset of this launch (chained launches)
     uint32_t *total_words;     // device scalar: base + compressed words of the whole range
+    uint32_t *total_host;      // nullable: mapped pinned host word that receives the same total (pipelined offloader: the
+                               // host sizes the chunk's D2H copy from it without a copy node in the compute stream)
     uint32_t *length_out;      // nullable: receives length_add + total
     uint32_t length_add;
     uint64_t *desc;            // decoupled look-back descriptors, >= count entries

@@ -31,7 +31,7 @@ tc = timed(lambda: off.compress(h, shape, h_stream)); td = timed(lambda: off.dec
 sb = n * 4
 print("offloader compress: %.2f ms (in %.1f GB/s, out %.0f MB)   decompress: %.2f ms (out %.1f GB/s)   round trip %.1f GB/s" % (
     tc * 1e3, nbytes / tc / 1e9, sb / 1e6, td * 1e3, nbytes / td / 1e9, nbytes / (tc + td) / 1e9))
-for cb in (4, 8, 16, 32, 64):
+for cb in (16, 32, 64, 128):
     os.environ["NDZB_CHUNK_BYTES"] = str(cb << 20)
     off2 = nz.make_cuda_offloader(dtype, 3)
     off2.compress(h, shape, h_stream); off2.decompress(h_stream, n, h2, shape)
