@@ -493,6 +493,9 @@ def main():
     from ndzip_b200 import dist as nzd
 
     torch.cuda.set_device(local_rank)
+    # host placement: this rank's thread and the pinned buffers it allocates go to the NUMA node of its GPU
+    # (ndzb_bind_host_to_device; -1 = the box exposes no NUMA topology, nothing changed)
+    numa_node = nz.bind_host_to_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -701,7 +704,7 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": e2e_ms, "api": "make_cuda_offloader(...).compress/.decompress (pinned host buffers)",
                "pcie_ceiling_gbs": nbytes_rank * world / (ceil_ms * 1e-3) / 1e9, "pcie_ceiling_ms": ceil_ms,
-               "frac_of_ceiling": ceil_ms / e2e_ms,
+               "frac_of_ceiling": ceil_ms / e2e_ms, "host_numa_node": numa_node,
                "pcie_ceiling_how": "pinned cudaMemcpyAsync of the same byte counts, H2D and D2H on two streams at once, "
                                    "compress-call pair + decompress-call pair, all ranks simultaneously"}
         del h_in, h_stream, h_back, off

@@ -84,6 +84,16 @@ int ndzb_offload_decompress(ndzb_ctx *ctx, const void *h_stream, uint32_t length
 int ndzb_host_alloc(void **out_ptr, size_t bytes);
 void ndzb_host_free(void *ptr);
 
+/* Host placement on multi-socket boxes (new work; the reference has no multi-GPU host side). On an 8-GPU node half of
+ * the GPUs hang off the other socket: a rank whose staging buffers sit on the wrong NUMA node moves every host<->device
+ * byte across the socket interconnect, which all such ranks share. ndzb_device_numa_node returns the NUMA node of CUDA
+ * device `device` (sysfs numa_node of its PCI function; -1 if unknown or not a NUMA box). ndzb_bind_host_to_device
+ * restricts the calling thread to that node's cores and makes the node the preferred source of new pages — call it
+ * once per rank BEFORE allocating pinned buffers (ndzb_host_alloc, cudaHostAlloc). Returns the node, or -1 if nothing
+ * was changed (unknown node, or the container forbids sched_setaffinity). */
+int ndzb_device_numa_node(int device);
+int ndzb_bind_host_to_device(int device);
+
 /* Multi-GPU sharding (new work; nothing to replace in the reference).
  * A rank compresses the hypercube range [hc_begin, hc_end) of the global array `size` that is fully
  * resident on its device (`d_data` points at the global array's element 0 as seen by this rank, i.e.

@@ -7,11 +7,13 @@ the built library.
 """
 from .api import (  # noqa: F401
     NdzipB200Error,
+    bind_host_to_device,
     compressed_length_bound,
     compressor_requirements,
     cuda_compressor,
     cuda_decompressor,
     cuda_offloader,
+    device_numa_node,
     make_cuda_compressor,
     make_cuda_decompressor,
     make_cuda_offloader,

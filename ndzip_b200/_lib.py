@@ -23,6 +23,8 @@ SYMBOLS = [
     ("ndzb_offload_decompress", _i, [_vp, _vp, _u32, _vp, _i, _vp, _pu32, _pu64]),
     ("ndzb_host_alloc", _i, [ctypes.POINTER(_vp), ctypes.c_size_t]),
     ("ndzb_host_free", None, [_vp]),
+    ("ndzb_device_numa_node", _i, [_i]),
+    ("ndzb_bind_host_to_device", _i, [_i]),
     ("ndzb_compress_cubes", _i, [_vp, _vp, _i, _vp, _u32, _u32, _vp, _vp, _vp]),
     ("ndzb_add_offset", _i, [_vp, _vp, _u32, _vp]),
     ("ndzb_fixup_header", _i, [_vp, _vp, _vp, _u32, _vp, _vp, _u32]),

@@ -216,6 +216,17 @@ class cuda_offloader(_context):
         return consumed.value
 
 
+def device_numa_node(device: int) -> int:
+    """NUMA node of CUDA device `device` (-1: unknown / not a NUMA box). ndzb_device_numa_node."""
+    return int(_lib.load().ndzb_device_numa_node(int(device)))
+
+
+def bind_host_to_device(device: int) -> int:
+    """Restrict this process to the cores of the device's NUMA node and prefer its memory for new pages; call once per
+    rank before allocating pinned buffers. Returns the node or -1 (nothing changed). ndzb_bind_host_to_device."""
+    return int(_lib.load().ndzb_bind_host_to_device(int(device)))
+
+
 def make_cuda_compressor(dtype, requirements: Union[compressor_requirements, Sequence[int]], stream=None) -> cuda_compressor:
     """reference include/ndzip/cuda.hh:36-38, src/ndzip/cuda_factory.cu:4-9"""
     if not isinstance(requirements, compressor_requirements):

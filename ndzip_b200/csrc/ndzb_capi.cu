@@ -13,6 +13,11 @@
 #include <new>
 #include <vector>
 
+#include <cctype>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 using namespace ndzb;
 
 namespace {
@@ -718,6 +723,64 @@ int ndzb_host_alloc(void **out_ptr, size_t bytes) {
 
 void ndzb_host_free(void *ptr) {
     if (ptr) cudaFreeHost(ptr);
+}
+
+// NUMA node of a CUDA device from sysfs (/sys/bus/pci/devices/<domain:bus:dev.fn>/numa_node); -1 if unknown.
+static int device_numa_node(int device) {
+    char bus_id[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus_id, sizeof bus_id, device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char *c = bus_id; *c; ++c) *c = static_cast<char>(tolower(*c));
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus_id);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+int ndzb_device_numa_node(int device) { return device_numa_node(device); }
+
+int ndzb_bind_host_to_device(int device) {
+    const int node = device_numa_node(device);
+    if (node < 0) return -1;
+    // CPUs of the node: "0-15,64-79"
+    char path[128];
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    char list[4096] = {0};
+    const bool got = fgets(list, sizeof list, f) != nullptr;
+    fclose(f);
+    if (!got) return -1;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int cpus = 0;
+    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int n = sscanf(tok, "%d-%d", &a, &b);
+        if (n < 1) continue;
+        if (n == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c) {
+            CPU_SET(c, &set);
+            ++cpus;
+        }
+    }
+    if (cpus == 0) return -1;
+    // The calling thread (and the threads it starts) run on the node's cores; new pages — the pinned buffers allocated
+    // from here on — come from the node's memory. MPOL_PREFERRED rather than MPOL_BIND: a full node falls back instead
+    // of failing. Containers may refuse either call: report the node only if the affinity took.
+    if (sched_setaffinity(0, sizeof set, &set) != 0) return -1;
+    unsigned long mask[16] = {0};
+    if (node < static_cast<int>(sizeof mask * 8)) {
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof mask * 8);  // best effort
+    }
+    return node;
 }
 
 void ndzb_ctx_destroy(ndzb_ctx *ctx) {
