@@ -327,6 +327,73 @@ def pcie_ceiling(h2d_bytes, d2h_bytes, dev, reps=3):
     return best
 
 
+def sharded_container_record(nz, nzd, dist, dtype, global_shape, slab_shape, rank, world, dev, tbits, d_in, d_stream, n_words,
+                             d_global, total_words):
+    """N > 1: the headline grid through the sharded container instead of the gather. Timed with the wall clock (file
+    I/O), max over ranks: (a) D2H of the slab stream + pwrite of the rank's segment, (b) table read + the rank's segment
+    decoded from the (memory-mapped) container by ndzb_container_decompress_segment."""
+    import tempfile
+    import torch
+    itemsize = np.dtype(dtype).itemsize
+    need = int(world * n_words * itemsize * 1.2) + (1 << 20)
+    box = [None]
+    if rank == 0:
+        for cand in ("/dev/shm", tempfile.gettempdir()):
+            try:
+                st = os.statvfs(cand)
+                if st.f_bavail * st.f_frsize > 2 * need and os.access(cand, os.W_OK):
+                    box[0] = os.path.join(cand, f"ndzb_bench_{os.getpid()}.ndzs")
+                    break
+            except OSError:
+                pass
+    dist.broadcast_object_list(box, src=0)
+    path = box[0]
+    if path is None:
+        return {"skipped": "no writable directory with %d MB free" % (2 * need >> 20)}
+
+    def wall_max(t):
+        v = torch.tensor([t], dtype=torch.float64, device=dev)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    hdr = nzd.write_sharded(path, dtype, global_shape, d_stream[:n_words])  # collective; fails on every rank or on none
+    write_s = wall_max(time.perf_counter() - t0)
+    ok, same, err = False, None, None
+    t0 = time.perf_counter()
+    try:  # rank-local from here to the next collective: a failure is reported, not raised
+        h_back = torch.empty(slab_shape, dtype=d_in.dtype, pin_memory=True)
+        off = nz.make_cuda_offloader(dtype, len(slab_shape))
+        blob = np.memmap(path, dtype=np.uint8, mode="r")
+        nzd.decompress_segment(off, blob, rank, h_back)
+        read_local = time.perf_counter() - t0
+        ok = bool(torch.equal(h_back.view(tbits), d_in.cpu().view(tbits)))
+        if rank == 0:
+            stitched = torch.from_numpy(nzd.to_global_stream(blob).view(np.int32 if itemsize == 4 else np.int64))
+            same = bool(stitched.numel() == total_words and torch.equal(stitched.to(dev), d_global[:total_words]))
+            del stitched
+        del blob, off
+    except Exception as exc:
+        err, read_local = repr(exc)[:200], time.perf_counter() - t0
+    read_s = wall_max(read_local)
+    flags = torch.tensor([1 if ok else 0, 1 if (same or rank != 0) else 0], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0 and os.path.exists(path):
+        os.remove(path)
+    nbytes = int(np.prod(global_shape)) * itemsize
+    out = {"what": "every rank writes / reads / decodes its own segment of ONE container file; no offset exchange, no gather "
+                   "(ndzb_container_create_file, _write_segment, _decompress_segment, _to_global_stream)",
+           "file": os.path.dirname(path), "container_bytes": int(hdr.total_bytes), "segments": len(hdr.segments),
+           "write_ms": write_s * 1e3, "write_gbs": nbytes / write_s / 1e9,
+           "read_decompress_ms": read_s * 1e3, "read_decompress_gbs": nbytes / read_s / 1e9,
+           "segments_round_trip": bool(flags[0].item()), "single_stream_from_container_identical_to_gathered": bool(flags[1].item())}
+    if err:
+        out["error"] = err
+    return out
+
+
 def run_dist_config(name, world, rank, dev, steps=5, identity=True):
     """One multi-GPU BASELINE config through the library's data plane (ndzb_dist_*): every rank owns one slab of
     WORKLOADS[name] x world. Timed: compress + exchange + decompress, the same plus the final NCCL gather into a
@@ -627,6 +694,7 @@ def main():
 
     # ---- N > 1: final stream gather of the headline grid, timed and checked against ONE GPU compressing the whole grid
     headline_gather = None
+    sharded = None
     if world > 1:
         L = codec.layout
         d_global = torch.empty(int(L.global_bound_words), dtype=tbits, device=dev) if rank == 0 else None
@@ -663,6 +731,14 @@ def main():
                            "global_stream_identical": identical, "gather_path": codec.last_gather_path,
                            "note": "ndzb_dist_compress + ndzb_dist_gather into a pre-allocated buffer on rank 0; "
                                    "bounded by one GPU's NVLink ingest"}
+        # ---- the same grid without any gather: the sharded container (ndzb_container_*). Every rank
+        # writes its own slab stream into one file, reads it back and decodes it from the container; rank 0 converts
+        # the container to the single stream and compares it with the gathered one.
+        try:
+            sharded = sharded_container_record(nz, nzd, dist, dtype, global_shape, shape, rank, world, dev, tbits,
+                                               d_in, d_stream, n_words, d_global, int(total_words))
+        except Exception as exc:  # optional record: never lose the headline line
+            sharded = {"error": repr(exc)[:300]}
         del d_global
         torch.cuda.empty_cache()
 
@@ -757,6 +833,8 @@ def main():
         line["e2e"] = e2e
     if headline_gather:
         line["stream_gather"] = headline_gather
+    if sharded:
+        line["sharded_container"] = sharded
     if configs:
         line["configs"] = configs
     if ref_cuda:

@@ -37,8 +37,10 @@ typedef enum ndzb_status {
     NDZB_ERR_CAPACITY = -3,         /* more hypercubes than the context was created for (compressor_requirements) */
     NDZB_ERR_CUDA = -4,             /* a CUDA runtime/driver call failed; see ndzb_last_cuda_error() */
     NDZB_ERR_ALLOC = -5,
-    NDZB_ERR_CORRUPT_STREAM = -6    /* host-pointer decompression: the header is not monotonic, a cube exceeds its bound, or
-                                       the stream ends before header + cubes + border (nothing was enqueued) */
+    NDZB_ERR_CORRUPT_STREAM = -6,   /* host-pointer decompression: the header is not monotonic, a cube exceeds its bound, or
+                                       the stream ends before header + cubes + border (nothing was enqueued); also: not a
+                                       sharded container / corrupt or truncated segment table */
+    NDZB_ERR_IO = -7                /* ndzb_container_* file functions: open / read / write failed (errno is set) */
 } ndzb_status;
 
 /* Opaque per-stream context. Owns the scratch the reference's cuda_compressor_impl owns
@@ -187,6 +189,55 @@ int ndzb_dist_gather(ndzb_dist *d, const void *d_local_stream, void *d_global_st
 int ndzb_dist_last_gather_path(const ndzb_dist *d);
 /* NCCL / CUDA error text of the last failing ndzb_dist_* call on this thread. */
 const char *ndzb_dist_last_error(void);
+
+/* ---- Sharded stream container (new work; nothing to replace in the reference) ------------------
+ * Keeps every rank's SELF-CONTAINED slab stream (what ndzb_dist_compress / ndzb_compress produce for the slab) behind
+ * a segment table, so that a multi-GPU pipeline that compresses to storage and decompresses again needs neither the
+ * cross-rank offset exchange nor the gather to one root:
+ *   u32 magic "NDZS" | u32 version | u32 dtype | u32 dims | u32 size[3] | u32 segments
+ *   per segment: u32 slab_begin | u32 slab_end (dimension 0) | u64 stream_words | u64 byte_offset
+ *   the segments, each starting at a multiple of 16 bytes.
+ * Host code only. All functions validate what they read and return NDZB_ERR_CORRUPT_STREAM on anything that is not a
+ * well-formed container (bad magic / version, table beyond the buffer, slabs that do not tile dimension 0, misaligned or
+ * overlapping segments). */
+typedef struct ndzb_container_segment {
+    uint32_t slab_begin, slab_end;   /* [begin, end) along dimension 0 of the global grid */
+    uint64_t stream_words;           /* length of the slab's ndzip stream in words of the dtype */
+    uint64_t byte_offset;            /* where it starts in the container */
+} ndzb_container_segment;
+typedef struct ndzb_container_info {
+    int32_t dtype, dims;
+    uint32_t size[3];                /* extent of the whole grid (dims entries) */
+    uint32_t segments;
+    uint64_t header_bytes;           /* segment table incl. padding = offset of the first segment */
+    uint64_t total_bytes;            /* size of the container */
+} ndzb_container_info;
+
+uint64_t ndzb_container_header_bytes(uint32_t segments);
+/* Segment table for `segments` ranks that own the slabs of ndzb_dist_plan(…, world = segments, …) and whose slab streams
+ * are stream_words[r] words long (e.g. ndzb_dist_gathered_lengths). stream_words and out_segments may both be null to
+ * query header_bytes only. */
+int ndzb_container_plan(int dtype, int dims, const uint32_t *global_size, uint32_t segments, const uint64_t *stream_words,
+        ndzb_container_info *info, ndzb_container_segment *out_segments);
+int ndzb_container_encode_header(const ndzb_container_info *info, const ndzb_container_segment *segments, void *out, uint64_t out_bytes);
+/* Parses the table at the start of `buf` (any alignment). out_segments may be null (then only *info is filled: call
+ * again with info->segments entries); NDZB_ERR_CAPACITY if max_segments is too small. */
+int ndzb_container_decode_header(const void *buf, uint64_t bytes, ndzb_container_info *info, ndzb_container_segment *out_segments,
+        uint32_t max_segments);
+/* The reference's single stream of the whole grid from a container in host memory whose slabs are those of
+ * ndzb_dist_plan: header entries rebased by the lower ranks' cube words (reference src/ndzip/common.hh:342-358), cube
+ * and border segments concatenated in rank order. out_stream may be null to query *out_words. */
+int ndzb_container_to_global_stream(const void *container, uint64_t bytes, void *out_stream, uint64_t capacity_words, uint64_t *out_words);
+/* Files. One rank creates the file (table + final size), then every rank writes its own segment with pwrite() — no
+ * data passes through another rank; readers fetch the table and the segments they own. */
+int ndzb_container_create_file(const char *path, const ndzb_container_info *info, const ndzb_container_segment *segments);
+int ndzb_container_write_segment(const char *path, int dtype, const ndzb_container_segment *segment, const void *h_stream);
+int ndzb_container_read_header(const char *path, ndzb_container_info *info, ndzb_container_segment *out_segments, uint32_t max_segments);
+int ndzb_container_read_segment(const char *path, int dtype, const ndzb_container_segment *segment, void *h_out);
+/* Sharded decompression: segment `index` of a container in host memory -> its slab (host pointer, slab extent =
+ * [slab_end - slab_begin, size[1], size[2]]), through ndzb_offload_decompress on `ctx` (created for the container's
+ * dtype / dims and at least the slab's hypercubes). */
+int ndzb_container_decompress_segment(ndzb_ctx *ctx, const void *container, uint64_t bytes, uint32_t index, void *h_slab, uint64_t *kernel_ns);
 
 /* Device-side self tests of the scan primitives, the counterpart of the reference's src/test/cuda_bits_test.cu:37-114
  * (warp scan, hierarchical scan in isolation). ndzb_selftest_lookback runs the decoupled look-back of the compress

@@ -58,7 +58,29 @@ SYMBOLS = [
     ("ndzb_dist_gather", _i, [_vp, _vp, _vp, _i, _pu64]),
     ("ndzb_dist_last_error", ctypes.c_char_p, []),
     ("ndzb_dist_last_gather_path", _i, [_vp]),
+    # sharded stream container
+    ("ndzb_container_header_bytes", _u64, [_u32]),
+    ("ndzb_container_plan", _i, [_i, _i, _vp, _u32, _vp, _vp, _vp]),
+    ("ndzb_container_encode_header", _i, [_vp, _vp, _vp, _u64]),
+    ("ndzb_container_decode_header", _i, [_vp, _u64, _vp, _vp, _u32]),
+    ("ndzb_container_to_global_stream", _i, [_vp, _u64, _vp, _u64, _pu64]),
+    ("ndzb_container_create_file", _i, [ctypes.c_char_p, _vp, _vp]),
+    ("ndzb_container_write_segment", _i, [ctypes.c_char_p, _i, _vp, _vp]),
+    ("ndzb_container_read_header", _i, [ctypes.c_char_p, _vp, _vp, _u32]),
+    ("ndzb_container_read_segment", _i, [ctypes.c_char_p, _i, _vp, _vp]),
+    ("ndzb_container_decompress_segment", _i, [_vp, _vp, _u64, _u32, _vp, _pu64]),
 ]
+
+
+class ContainerSegment(ctypes.Structure):
+    """struct ndzb_container_segment (include/ndzip_b200.h)"""
+    _fields_ = [("slab_begin", _u32), ("slab_end", _u32), ("stream_words", _u64), ("byte_offset", _u64)]
+
+
+class ContainerInfo(ctypes.Structure):
+    """struct ndzb_container_info (include/ndzip_b200.h)"""
+    _fields_ = [("dtype", ctypes.c_int32), ("dims", ctypes.c_int32), ("size", _u32 * 3), ("segments", _u32),
+                ("header_bytes", _u64), ("total_bytes", _u64)]
 
 
 class DistLayout(ctypes.Structure):

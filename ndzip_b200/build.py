@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.environ.get("NDZB_CSRC") or os.path.join(HERE, "csrc")  # NDZB_CSRC: build another revision of the sources (A/B runs)
 LIB = os.path.join(HERE, "libndzip_b200.so")
-SOURCES = ["ndzb_kernels.cu", "ndzb_capi.cu", "ndzb_dist.cu", "ndzip_adapter.cu"]
+SOURCES = ["ndzb_kernels.cu", "ndzb_capi.cu", "ndzb_dist.cu", "ndzb_container.cu", "ndzip_adapter.cu"]
 HEADERS = ["ndzb_cube.cuh", "ndzb_ptx.cuh", "ndzb_kernels.cuh"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -1117,6 +1117,7 @@ const char *ndzb_strerror(int status) {
         case NDZB_ERR_CUDA: return "CUDA error";
         case NDZB_ERR_ALLOC: return "out of memory";
         case NDZB_ERR_CORRUPT_STREAM: return "compressed input ends inside a stream or its header is corrupt";
+        case NDZB_ERR_IO: return "file input / output failed";
         default: return "unknown ndzb status";
     }
 }

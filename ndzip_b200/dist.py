@@ -234,9 +234,10 @@ def gather_global_stream(layout: ShardLayout, local_stream, fixed_header32, root
 #   per segment: u32 slab_begin | u32 slab_end (dimension 0) | u64 stream_words | u64 byte_offset
 #   segments, each starting at a multiple of 16 bytes
 #
+# The format, its validation, the conversion to the reference's single stream and the file I/O live in the
+# library (csrc/ndzb_container.cu, include/ndzip_b200.h ndzb_container_*); what follows is the ctypes mirror.
 # Writing needs one all-gather of the stream lengths (for the byte offsets); reading needs nothing: a
-# rank takes the segments whose slabs it owns, in any world size. `to_global_stream` converts to the
-# reference's single stream when one is wanted.
+# rank takes the segments whose slabs it owns, in any world size.
 
 SHARDED_MAGIC = 0x535A444E  # "NDZS" little endian
 SHARDED_VERSION = 1
@@ -259,7 +260,8 @@ class ShardedHeader:
 
     @property
     def header_bytes(self) -> int:
-        return _align16(4 * (_FIXED_WORDS + _SEGMENT_WORDS * len(self.segments)))
+        from . import _lib
+        return int(_lib.load().ndzb_container_header_bytes(len(self.segments)))
 
     @property
     def total_bytes(self) -> int:
@@ -272,63 +274,85 @@ class ShardedHeader:
         return slab_shape(self.shape, self.segments[i].slab)
 
 
-def _align16(n: int) -> int:
-    return (n + 15) // 16 * 16
+def _container_error(status: int, what: str):
+    """ValueError for anything that is not a well-formed container, like the Python prototype raised."""
+    from . import _lib
+    msg = _lib.load().ndzb_strerror(status).decode()
+    return ValueError(f"{what}: {msg}") if status in (-6, -1, -3) else OSError(f"{what}: {msg}")
+
+
+def _c_structs(hdr: ShardedHeader):
+    import ctypes
+    from . import _lib
+    info = _lib.ContainerInfo()
+    info.dtype = 0 if hdr.dtype == "float32" else 1
+    info.dims = len(hdr.shape)
+    for d, n in enumerate(hdr.shape):
+        info.size[d] = int(n)
+    info.segments = len(hdr.segments)
+    info.header_bytes = hdr.header_bytes
+    info.total_bytes = hdr.total_bytes
+    segs = (_lib.ContainerSegment * max(1, len(hdr.segments)))()
+    for i, s in enumerate(hdr.segments):
+        segs[i].slab_begin, segs[i].slab_end = s.slab
+        segs[i].stream_words = s.stream_words
+        segs[i].byte_offset = s.byte_offset
+    return info, segs, ctypes
+
+
+def _from_c(info, segs) -> ShardedHeader:
+    return ShardedHeader("float32" if info.dtype == 0 else "float64", tuple(int(info.size[d]) for d in range(info.dims)),
+                         [Segment((int(s.slab_begin), int(s.slab_end)), int(s.stream_words), int(s.byte_offset))
+                          for s in segs[: info.segments]])
 
 
 def sharded_header(dtype, global_shape: Sequence[int], stream_words: Sequence[int]) -> ShardedHeader:
-    """Segment table for `len(stream_words)` ranks that own the slabs of slab_partition()."""
-    dtype = np.dtype(dtype).name
-    item = np.dtype(dtype).itemsize
-    spans = slab_partition(global_shape, len(stream_words))
-    hdr = ShardedHeader(dtype, tuple(int(x) for x in global_shape), [])
-    offset = _align16(4 * (_FIXED_WORDS + _SEGMENT_WORDS * len(stream_words)))
-    for span, words in zip(spans, stream_words):
-        hdr.segments.append(Segment(span, int(words), offset))
-        offset = _align16(offset + int(words) * item)
-    return hdr
+    """Segment table for `len(stream_words)` ranks that own the slabs of slab_partition(). ndzb_container_plan."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    n = len(stream_words)
+    dims, sz = _lib.size3(tuple(int(x) for x in global_shape))
+    words = (ctypes.c_uint64 * max(1, n))(*[int(w) for w in stream_words])
+    info = _lib.ContainerInfo()
+    segs = (_lib.ContainerSegment * max(1, n))()
+    rc = lib.ndzb_container_plan(0 if np.dtype(dtype).itemsize == 4 else 1, dims, sz, n, words, ctypes.byref(info), segs)
+    if rc:
+        raise _container_error(rc, "ndzb_container_plan")
+    return _from_c(info, segs)
 
 
 def encode_sharded_header(hdr: ShardedHeader) -> bytes:
-    dims = len(hdr.shape)
-    words = [SHARDED_MAGIC, SHARDED_VERSION, 0 if hdr.dtype == "float32" else 1, dims]
-    words += list(hdr.shape) + [0] * (3 - dims) + [len(hdr.segments)]
-    for s in hdr.segments:
-        words += [s.slab[0], s.slab[1], s.stream_words & 0xffffffff, s.stream_words >> 32,
-                  s.byte_offset & 0xffffffff, s.byte_offset >> 32]
-    raw = np.asarray(words, dtype=np.uint32).tobytes()
-    return raw + b"\0" * (hdr.header_bytes - len(raw))
+    """ndzb_container_encode_header"""
+    from . import _lib
+    info, segs, ctypes = _c_structs(hdr)
+    out = ctypes.create_string_buffer(hdr.header_bytes)
+    rc = _lib.load().ndzb_container_encode_header(ctypes.byref(info), segs, out, hdr.header_bytes)
+    if rc:
+        raise _container_error(rc, "ndzb_container_encode_header")
+    return out.raw
+
+
+def _as_u8(buf) -> np.ndarray:
+    return np.ascontiguousarray(np.frombuffer(buf, dtype=np.uint8))
 
 
 def decode_sharded_header(buf) -> ShardedHeader:
     """Parses the table at the start of a container (bytes / memoryview / uint8 array); raises ValueError on
-    anything that is not one."""
-    raw = np.frombuffer(buf, dtype=np.uint8)
-    if raw.size < 4 * _FIXED_WORDS:
-        raise ValueError("not an ndzip sharded stream: too short")
-    fixed = raw[: 4 * _FIXED_WORDS].view(np.uint32)
-    if int(fixed[0]) != SHARDED_MAGIC:
-        raise ValueError("not an ndzip sharded stream: bad magic")
-    if int(fixed[1]) != SHARDED_VERSION:
-        raise ValueError(f"unsupported sharded stream version {int(fixed[1])}")
-    dtype_code, dims, count = int(fixed[2]), int(fixed[3]), int(fixed[7])
-    if dtype_code not in (0, 1) or not 1 <= dims <= 3:
-        raise ValueError("corrupt sharded stream header")
-    need = 4 * (_FIXED_WORDS + _SEGMENT_WORDS * count)
-    if raw.size < need:
-        raise ValueError("truncated sharded stream header")
-    table = raw[4 * _FIXED_WORDS: need].view(np.uint32).reshape(count, _SEGMENT_WORDS)
-    hdr = ShardedHeader("float32" if dtype_code == 0 else "float64", tuple(int(x) for x in fixed[4: 4 + dims]), [])
-    end_of_previous = 0
-    for row in table:
-        seg = Segment((int(row[0]), int(row[1])), int(row[2]) | (int(row[3]) << 32), int(row[4]) | (int(row[5]) << 32))
-        if seg.slab[0] != end_of_previous or seg.slab[1] < seg.slab[0] or seg.byte_offset % 16:
-            raise ValueError("corrupt sharded stream segment table")
-        end_of_previous = seg.slab[1]
-        hdr.segments.append(seg)
-    if count and end_of_previous != hdr.shape[0]:
-        raise ValueError("sharded stream segments do not cover the grid")
-    return hdr
+    anything that is not one. ndzb_container_decode_header."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    raw = _as_u8(buf)
+    info = _lib.ContainerInfo()
+    rc = lib.ndzb_container_decode_header(raw.ctypes.data, raw.size, ctypes.byref(info), None, 0)
+    if rc:
+        raise _container_error(rc, "not an ndzip sharded stream")
+    segs = (_lib.ContainerSegment * info.segments)()
+    rc = lib.ndzb_container_decode_header(raw.ctypes.data, raw.size, ctypes.byref(info), segs, info.segments)
+    if rc:
+        raise _container_error(rc, "not an ndzip sharded stream")
+    return _from_c(info, segs)
 
 
 def pack_sharded(dtype, global_shape: Sequence[int], local_streams: Sequence[np.ndarray]) -> bytes:
@@ -364,21 +388,45 @@ def segments_of_rank(hdr: ShardedHeader, rank: int, world_size: int) -> List[int
 
 def to_global_stream(buf) -> np.ndarray:
     """The reference's single stream of the whole grid, from a container whose slabs are those of
-    slab_partition(shape, segments) (what write_sharded / pack_sharded produce)."""
-    hdr = decode_sharded_header(buf)
-    spans = slab_partition(hdr.shape, len(hdr.segments))
-    if [s.slab for s in hdr.segments] != spans:
+    slab_partition(shape, segments) (what write_sharded / pack_sharded produce). ndzb_container_to_global_stream."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    raw = _as_u8(buf)
+    hdr = decode_sharded_header(raw)
+    bits = np.uint32 if hdr.dtype == "float32" else np.uint64
+    words = ctypes.c_uint64(0)
+    rc = lib.ndzb_container_to_global_stream(raw.ctypes.data, raw.size, None, 0, ctypes.byref(words))
+    if rc == -1:
         raise ValueError("segments are not the slabs of slab_partition(); decode them one by one instead")
-    return stitch_global_stream(hdr.dtype, hdr.shape, [sharded_segment(buf, hdr, i) for i in range(len(hdr.segments))])
+    if rc:
+        raise _container_error(rc, "ndzb_container_to_global_stream")
+    out = np.empty(words.value, dtype=bits)
+    rc = lib.ndzb_container_to_global_stream(raw.ctypes.data, raw.size, out.ctypes.data, out.size, ctypes.byref(words))
+    if rc:
+        raise _container_error(rc, "ndzb_container_to_global_stream")
+    return out
+
+
+def decompress_segment(offloader, buf, index: int, out_slab) -> None:
+    """Sharded decompression: segment `index` of a container in host memory -> its slab (numpy array or pinned torch
+    tensor of the slab's shape) on the GPU behind `offloader` (make_cuda_offloader). ndzb_container_decompress_segment."""
+    from . import _lib
+    raw = _as_u8(buf)
+    ptr = out_slab.ctypes.data if isinstance(out_slab, np.ndarray) else out_slab.data_ptr()
+    _lib.check(_lib.load().ndzb_container_decompress_segment(offloader._handle, raw.ctypes.data, raw.size, int(index), ptr, None))
 
 
 def write_sharded(path: str, dtype, global_shape: Sequence[int], local_stream, group=None) -> ShardedHeader:
-    """Collective: every rank writes its own segment of the container at `path` (a file all ranks can reach).
-    `local_stream`: the rank's complete local stream (numpy bits array, or a torch tensor on any device — it is
-    brought to the host here). The only communication is one all-gather of the stream lengths."""
+    """Collective: every rank writes its own segment of the container at `path` (a file all ranks can reach) with
+    pwrite() — ndzb_container_create_file on rank 0, ndzb_container_write_segment everywhere. `local_stream`: the rank's
+    complete local stream (numpy bits array, or a torch tensor on any device — it is brought to the host here). The
+    only communication is one all-gather of the stream lengths."""
     import torch
     import torch.distributed as dist
+    from . import _lib
 
+    lib = _lib.load()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     if isinstance(local_stream, torch.Tensor):
@@ -387,6 +435,8 @@ def write_sharded(path: str, dtype, global_shape: Sequence[int], local_stream, g
     else:
         host = np.ascontiguousarray(local_stream)
         device = "cpu"
+    if world > 1 and device == "cpu" and dist.get_backend(group) == "nccl":
+        device = torch.device("cuda", torch.cuda.current_device())  # NCCL moves device tensors only
     mine = torch.tensor([int(host.size)], dtype=torch.int64, device=device)
     if world > 1:
         gathered = torch.empty(world, dtype=torch.int64, device=mine.device)
@@ -394,40 +444,50 @@ def write_sharded(path: str, dtype, global_shape: Sequence[int], local_stream, g
     else:
         gathered = mine
     hdr = sharded_header(dtype, global_shape, [int(w) for w in gathered.cpu().tolist()])
-    if rank == 0:
-        with open(path, "wb") as f:
-            f.write(encode_sharded_header(hdr))
-            f.truncate(hdr.total_bytes)
-    if world > 1:
-        dist.barrier(group=group)
-    seg = hdr.segments[rank]
-    with open(path, "r+b") as f:
-        f.seek(seg.byte_offset)
-        f.write(host.tobytes())
-    if world > 1:
-        dist.barrier(group=group)
+    info, segs, ctypes = _c_structs(hdr)
+
+    def agree(rc: int) -> int:
+        """Every rank learns the worst status (instead of a bare barrier: a rank that failed must not leave the others
+        waiting in the next collective)."""
+        if world == 1:
+            return rc
+        t = torch.tensor([rc], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        return int(t.item())
+
+    rc = lib.ndzb_container_create_file(path.encode(), ctypes.byref(info), segs) if rank == 0 else 0
+    rc = agree(rc)
+    if rc:
+        raise _container_error(rc, f"creating {path}")
+    rc = agree(lib.ndzb_container_write_segment(path.encode(), info.dtype, ctypes.byref(segs[rank]), host.ctypes.data))
+    if rc:
+        raise _container_error(rc, f"writing the segments of {path}")
     return hdr
 
 
 def read_sharded(path: str, rank: int = 0, world_size: int = 1):
-    """The segments a rank owns: [(slab span, slab shape, stream words as numpy bits array), ...]. No communication."""
-    with open(path, "rb") as f:
-        head = f.read(4 * _FIXED_WORDS)
-        count = int(np.frombuffer(head, dtype=np.uint32)[7]) if len(head) == 4 * _FIXED_WORDS else 0
-        # the count comes from the file: never read more table than the file can hold
-        import os
-        count = min(count, max(0, os.fstat(f.fileno()).st_size - len(head)) // (4 * _SEGMENT_WORDS) + 1)
-        head += f.read(4 * _SEGMENT_WORDS * count)
-        hdr = decode_sharded_header(head)
-        bits = np.uint32 if hdr.dtype == "float32" else np.uint64
-        out = []
-        for i in segments_of_rank(hdr, rank, world_size):
-            seg = hdr.segments[i]
-            f.seek(seg.byte_offset)
-            raw = f.read(seg.stream_words * np.dtype(bits).itemsize)
-            if len(raw) != seg.stream_words * np.dtype(bits).itemsize:
-                raise ValueError("truncated sharded stream")
-            out.append((seg.slab, hdr.slab_shape(i), np.frombuffer(raw, dtype=bits)))
+    """The segments a rank owns: [(slab span, slab shape, stream words as numpy bits array), ...]. No communication.
+    ndzb_container_read_header / ndzb_container_read_segment."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    info = _lib.ContainerInfo()
+    rc = lib.ndzb_container_read_header(path.encode(), ctypes.byref(info), None, 0)
+    if rc:
+        raise _container_error(rc, f"reading {path}")
+    segs = (_lib.ContainerSegment * info.segments)()
+    rc = lib.ndzb_container_read_header(path.encode(), ctypes.byref(info), segs, info.segments)
+    if rc:
+        raise _container_error(rc, f"reading {path}")
+    hdr = _from_c(info, segs)
+    bits = np.uint32 if hdr.dtype == "float32" else np.uint64
+    out = []
+    for i in segments_of_rank(hdr, rank, world_size):
+        words = np.empty(hdr.segments[i].stream_words, dtype=bits)
+        rc = lib.ndzb_container_read_segment(path.encode(), info.dtype, ctypes.byref(segs[i]), words.ctypes.data)
+        if rc:
+            raise ValueError("truncated sharded stream") if rc == -6 else _container_error(rc, f"reading segment {i} of {path}")
+        out.append((hdr.segments[i].slab, hdr.slab_shape(i), words))
     return hdr, out
 
 

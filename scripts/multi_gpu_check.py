@@ -50,6 +50,38 @@ def check_case(dtype, shape, rank, world, dev):
         same = n == total and bool(torch.equal(ref[:n], d_global[:n]))
         ok = ok and same
         print(f"{dtype} {shape}: global stream {total} words, single-GPU {n} words, identical={same}, gather via {path}", flush=True)
+    # ---- sharded container: no offset exchange, no gather. Every rank writes its own slab stream into
+    # one file (ndzb_container_create_file / _write_segment), reads the table back, decodes ITS segment from the
+    # container with ndzb_container_decompress_segment, and rank 0 converts the container to the single stream
+    # (ndzb_container_to_global_stream), which must be the gathered one.
+    n_local = int(d_len.cpu().numpy().view(np.uint32)[0])
+    box = [None]
+    if rank == 0:
+        import tempfile
+        box[0] = os.path.join(tempfile.gettempdir(), f"ndzb_check_{os.getpid()}.ndzs")
+    dist.broadcast_object_list(box, src=0)
+    path = box[0]
+    hdr = nzd.write_sharded(path, dtype, shape, d_stream[:n_local])
+    blob = np.fromfile(path, dtype=np.uint8)
+    hdr2, mine = nzd.read_sharded(path, rank, world)
+    seg_ok = len(mine) == 1 and mine[0][0] == (L.slab_begin, L.slab_end) and np.array_equal(
+        mine[0][2].view(np.uint8), d_stream[:n_local].cpu().numpy().view(np.uint8))
+    h_slab = np.zeros(tuple(slab.shape), dtype=dtype)
+    if slab.numel():
+        off = nz.make_cuda_offloader(dtype, len(shape))
+        nzd.decompress_segment(off, blob, rank, h_slab)
+        off.close()
+    seg_ok = seg_ok and h_slab.tobytes() == slab.cpu().numpy().tobytes() and hdr2.total_bytes == blob.size == hdr.total_bytes
+    if rank == 0:
+        stitched = nzd.to_global_stream(blob)
+        same = stitched.size == total and np.array_equal(stitched.view(np.uint8), d_global[:total].cpu().numpy().view(np.uint8))
+        seg_ok = seg_ok and same
+        print(f"    container: {hdr.total_bytes} bytes in {len(hdr.segments)} segments, every rank decoded its own; "
+              f"single stream from the container identical={same}", flush=True)
+    dist.barrier()
+    if rank == 0:
+        os.remove(path)
+    ok = ok and bool(seg_ok)
     codec.close()
     return ok
 

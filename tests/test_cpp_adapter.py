@@ -91,3 +91,23 @@ def test_dist_program_passes_on_all_visible_gpus():
         exe = _build_dist()
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "PASS" in res.stdout, res.stdout + res.stderr
+
+
+# ---- sharded stream container through the C ABI from plain C (tests/cpp/container_test.c): host only, runs here ----
+
+def test_container_program_in_c_passes(tmp_path):
+    from ndzip_b200 import build as nzbuild
+    import oracle
+    nzbuild.build()
+    oracle.build("oracle")
+    os.makedirs(BUILD, exist_ok=True)
+    out = os.path.join(BUILD, "container_test")
+    libdir = os.path.join(ROOT, "ndzip_b200")
+    oradir = os.path.join(ROOT, "oracle")
+    cmd = ["gcc", "-std=c11", "-O1", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "tests", "cpp", "container_test.c"),
+           f"-I{ROOT}/include", "-o", out, f"-L{libdir}", "-lndzip_b200", f"-L{oradir}", "-lndzip_oracle",
+           f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{oradir}"]
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run(cmd, check=True, env=env)
+    res = subprocess.run([out, str(tmp_path / "c.ndzs")], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "PASS" in res.stdout, res.stdout + res.stderr

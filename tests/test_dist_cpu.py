@@ -127,6 +127,73 @@ def test_sharded_container_rejects_garbage(oracle):
     assert [nzd.segments_of_rank(nzd.sharded_header("float32", (4096 * 8,), [1] * 8), r, 3) for r in range(3)] == [[0, 1], [2, 3, 4], [5, 6, 7]]
 
 
+def test_sharded_container_table_is_validated_by_the_library(oracle):
+    # ndzb_container_decode_header / ndzb_container_to_global_stream (csrc/ndzb_container.cu): every way a table can lie
+    shape = (4096 * 6,)
+    data = synth.hashed(shape, "float32", seed=5)
+    spans = nzd.slab_partition(shape, 3)
+    local = [oracle.compress(np.ascontiguousarray(data[b:e])) for b, e in spans]
+    good = nzd.pack_sharded("float32", shape, local)
+    hdr = nzd.decode_sharded_header(good)
+    words = np.frombuffer(good, dtype=np.uint32).copy()
+
+    def table(seg, field):  # u32 index of a table field: begin 0, end 1, words 2-3, offset 4-5
+        return 8 + 6 * seg + field
+
+    def broken(index, value):
+        w = words.copy()
+        w[index] = value
+        return w.tobytes()
+
+    for bad in (
+        broken(table(1, 0), hdr.segments[1].slab[0] + 4096),           # slabs do not tile dimension 0
+        broken(table(2, 1), hdr.segments[2].slab[1] - 4096),           # ... or do not reach its end
+        broken(table(1, 4), hdr.segments[1].byte_offset + 4),          # misaligned segment
+        broken(table(1, 4), hdr.segments[0].byte_offset),              # overlapping segments
+        broken(7, 1 << 24),                                            # absurd segment count
+        broken(7, 4),                                                  # table longer than it is
+        broken(3, 4), broken(2, 2),                                    # dims / dtype out of range
+    ):
+        with pytest.raises(ValueError):
+            nzd.decode_sharded_header(bad)
+    with pytest.raises(ValueError):   # a segment that ends beyond the buffer
+        nzd.to_global_stream(good[:-16])
+    w = words.copy()                  # a slab stream whose own header disagrees with the segment length
+    w[hdr.segments[1].byte_offset // 4 + nzd.cubes_in((spans[1][1] - spans[1][0],)) - 1] += 1
+    with pytest.raises(ValueError):
+        nzd.to_global_stream(w.tobytes())
+    # slabs other than the library's own partition cannot be concatenated (they can still be decoded one by one)
+    first = 80  # header of two segments: 4 * (8 + 2 * 6) = 80 bytes
+    uneven = nzd.ShardedHeader("float32", shape, [nzd.Segment((0, 4096), local[0].size, first),
+                                                  nzd.Segment((4096, shape[0]), 0, first + 4 * ((local[0].size + 3) // 4 * 4))])
+    blob = bytearray(uneven.total_bytes)
+    blob[: len(nzd.encode_sharded_header(uneven))] = nzd.encode_sharded_header(uneven)
+    assert len(nzd.decode_sharded_header(bytes(blob)).segments) == 2
+    with pytest.raises(ValueError):
+        nzd.to_global_stream(bytes(blob))
+    # unaligned buffers parse (the table is read with memcpy)
+    shifted = np.frombuffer(b"x" + good, dtype=np.uint8)[1:]
+    assert nzd.decode_sharded_header(shifted).segments == hdr.segments
+
+
+def test_sharded_container_files_fail_cleanly(tmp_path, oracle):
+    with pytest.raises(OSError):
+        nzd.read_sharded(str(tmp_path / "missing.ndzs"))
+    junk = tmp_path / "junk.ndzs"
+    junk.write_bytes(b"NDZS" + bytes(60))
+    with pytest.raises(ValueError):
+        nzd.read_sharded(str(junk))
+    data = synth.hashed((4096 * 2,), "float32", seed=6)
+    path = str(tmp_path / "one.ndzs")
+    nzd.write_sharded(path, "float32", data.shape, oracle.compress(data))
+    hdr, segs = nzd.read_sharded(path)
+    assert len(segs) == 1 and np.array_equal(segs[0][2], oracle.compress(data))
+    with open(path, "r+b") as f:   # file cut inside the segment
+        f.truncate(hdr.total_bytes - 8)
+    with pytest.raises(ValueError):
+        nzd.read_sharded(path)
+
+
 def _container_worker(rank, world, port, dtype, shape, path):
     import torch.distributed as dist
     from oracle import get_oracle

@@ -559,6 +559,15 @@ def test_sharded_container_of_gpu_streams(nz, dtype, shape):
     whole, _ = gpu_compress(data)
     assert np.array_equal(nzd.to_global_stream(buf), whole)
     assert np.array_equal(whole, get_oracle().compress(data))
+    # sharded decompression through the C ABI: ndzb_container_decompress_segment reads the segment out of the container
+    off = nz.make_cuda_offloader(dtype, len(shape))
+    for i, (b, e) in enumerate(spans):
+        out = np.zeros(hdr.slab_shape(i), dtype=dtype)
+        nzd.decompress_segment(off, buf, i, out)
+        assert out.tobytes() == data[b:e].tobytes()
+    # a container whose segment is cut short fails before anything reaches the device
+    with pytest.raises(nz.NdzipB200Error):
+        nzd.decompress_segment(off, buf[: hdr.segments[-1].byte_offset + 8], len(spans) - 1, np.zeros(hdr.slab_shape(len(spans) - 1), dtype=dtype))
 
 
 # ---- reference "Residual encodings equivalent" (src/test/codec_profile_test.inl:552-729): a cube whose RESIDUALS are
