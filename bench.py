@@ -356,16 +356,18 @@ def sharded_container_record(nz, nzd, dist, dtype, global_shape, slab_shape, ran
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         return float(v.item())
 
+    h_stream = torch.empty(n_words, dtype=tbits, pin_memory=True)   # staging buffers and the offloader: not timed
+    h_back = torch.empty(slab_shape, dtype=d_in.dtype, pin_memory=True)
+    off = nz.make_cuda_offloader(dtype, len(slab_shape))
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
-    hdr = nzd.write_sharded(path, dtype, global_shape, d_stream[:n_words])  # collective; fails on every rank or on none
+    h_stream.copy_(d_stream[:n_words])
+    hdr = nzd.write_sharded(path, dtype, global_shape, h_stream.numpy())  # collective; fails on every rank or on none
     write_s = wall_max(time.perf_counter() - t0)
     ok, same, err = False, None, None
     t0 = time.perf_counter()
     try:  # rank-local from here to the next collective: a failure is reported, not raised
-        h_back = torch.empty(slab_shape, dtype=d_in.dtype, pin_memory=True)
-        off = nz.make_cuda_offloader(dtype, len(slab_shape))
         blob = np.memmap(path, dtype=np.uint8, mode="r")
         nzd.decompress_segment(off, blob, rank, h_back)
         read_local = time.perf_counter() - t0
@@ -374,7 +376,7 @@ def sharded_container_record(nz, nzd, dist, dtype, global_shape, slab_shape, ran
             stitched = torch.from_numpy(nzd.to_global_stream(blob).view(np.int32 if itemsize == 4 else np.int64))
             same = bool(stitched.numel() == total_words and torch.equal(stitched.to(dev), d_global[:total_words]))
             del stitched
-        del blob, off
+        del blob
     except Exception as exc:
         err, read_local = repr(exc)[:200], time.perf_counter() - t0
     read_s = wall_max(read_local)
