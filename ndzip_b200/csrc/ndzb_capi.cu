@@ -561,13 +561,20 @@ int pipelined_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uint32
     // (total_host), so the compute stream holds nothing but kernels. (A 4-byte D2H copy node per chunk in that stream
     // queued behind the large copies of the copy-out stream on the same copy engine and stalled every later kernel:
     // profiles/README.md, round 2, "offloader timeline".) One host synchronisation per chunk; the host has nothing else to do.
+    // Every copy but the last ends on a 4 KiB boundary of the stream (the few words beyond it travel with the next
+    // chunk), so that all copies start aligned on both sides.
     uint32_t prev = 0;
+    size_t sent = static_cast<size_t>(hdr) * wb;  // bytes of the stream already on their way (the header goes last)
     for (int c = 0; c < plan.chunks; ++c) {
         NDZB_CUDA(cudaEventSynchronize(ctx->ev_done[c]));
         trace.mark_host();
         const uint32_t tot = *static_cast<volatile uint32_t *>(ctx->h_totals + c);
-        const size_t off = (static_cast<size_t>(hdr) + prev) * wb;
-        if (tot > prev) NDZB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, static_cast<size_t>(tot - prev) * wb, cudaMemcpyDeviceToHost, ctx->s_out));
+        size_t end = (static_cast<size_t>(hdr) + tot) * wb;
+        if (c + 1 < plan.chunks) end = end / 4096 * 4096;
+        if (end > sent) {
+            NDZB_CUDA(cudaMemcpyAsync(h_out + sent, d_out + sent, end - sent, cudaMemcpyDeviceToHost, ctx->s_out));
+            sent = end;
+        }
         trace.mark_out(c, ctx->s_out);
         prev = tot;
     }
@@ -605,7 +612,15 @@ int pipelined_decompress(ndzb_ctx *ctx, const void *h_stream, void *h_data, int 
         const uint32_t hb = row0 * plan.cubes_per_row, he = row1 * plan.cubes_per_row;
         const size_t w0 = static_cast<size_t>(hdr) + (hb ? h_offsets[hb - 1] : 0u);
         const size_t w1 = static_cast<size_t>(hdr) + h_offsets[he - 1];
-        NDZB_CUDA(cudaMemcpyAsync(d_stream + w0 * wb, h_in + w0 * wb, (w1 - w0) * wb, cudaMemcpyHostToDevice, ctx->s_in));
+        // The chunk's compressed cubes start and end at arbitrary words. The copy is widened to 4 KiB boundaries of the
+        // stream (re-sending a few bytes of the neighbouring chunks, which hold the same data on both sides): copies
+        // that start in the middle of a cache line move over PCIe at ~41 instead of ~50 GB/s next to a concurrent D2H
+        // (profiles/README.md, round 2, "offloader timeline").
+        constexpr size_t kAlign = 4096;
+        const size_t total_bytes = (static_cast<size_t>(hdr) + h_offsets[H - 1]) * wb;
+        size_t b0 = w0 * wb / kAlign * kAlign, b1 = (w1 * wb + kAlign - 1) / kAlign * kAlign;
+        if (b1 > total_bytes) b1 = total_bytes;
+        if (b1 > b0) NDZB_CUDA(cudaMemcpyAsync(d_stream + b0, h_in + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->s_in));
         trace.mark_in(c, ctx->s_in);
         NDZB_CUDA(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
         NDZB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0));
