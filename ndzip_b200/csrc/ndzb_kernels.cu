@@ -1857,7 +1857,15 @@ struct ws_variant {
 // statistics). Measured on
 // B200 with descriptors one per 64 bytes (profiles/README.md): float 5 groups + 4 retire warps + two-level look-back
 // (3-D 0.193 ms, 1-D 0.297 ms per GiB), double 3 + 2 with 32-cube windows (2-D 0.199 ms).
-#if defined(NDZB_TUNING)
+#if defined(NDZB_TUNING) && defined(NDZB_TUNING_SWEEP2)
+// second sweep of (groups, retire warps), with paired tickets, after the encoder got lighter (shuffle stencil)
+constexpr ws_variant kWsVariants32[] = {{5, 4, 0, -2, 0, 1, false, false}, {5, 5, 0, -2, 0, 1, false, false}, {4, 5, 0, -2, 0, 1, false, false},
+        {4, 4, 0, -2, 0, 1, false, false}, {5, 4, 0, 1, 0, 1, false, true}, {5, 3, 0, -2, 0, 1, false, false}, {4, 6, 0, -2, 0, 1, false, false},
+        {5, 4, 1, -2, 0, 1, false, false}};
+constexpr ws_variant kWsVariants64[] = {{3, 2, 1, 1, 0, 1, false, false}, {3, 3, 1, 1, 0, 1, false, false}, {3, 4, 1, 1, 0, 1, false, false},
+        {2, 3, 1, 1, 0, 1, false, false}, {3, 2, 1, 1, 0, 1, false, true}, {3, 2, 0, 1, 0, 1, false, false}, {3, 3, 0, 1, 0, 1, false, false},
+        {3, 2, 2, 1, 0, 1, false, false}};
+#elif defined(NDZB_TUNING)
 constexpr ws_variant kWsVariants32[] = {{5, 4, 0, 1, 0, 1, false, false}, {5, 4, 0, 1, 3, 1, false, false}, {5, 4, 0, 1, 2, 1, false, false},
         {5, 3, 0, 1, 3, 1, false, false}, {5, 4, 0, 1, 0, 1, false, true}, {4, 4, 0, 1, 4, 1, false, false}, {5, 3, 0, 1, 4, 1, false, false},
         {5, 5, 0, 1, 2, 1, false, false}};
