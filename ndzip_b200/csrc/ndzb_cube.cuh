@@ -196,6 +196,21 @@ template<> NDZB_HD int tile_elem<uint64_t>(int e) {
 struct alignas(16) quad { uint32_t x, y, z, w; };
 
 NDZB_HD quad ld_quad(const uint32_t *p) { return *reinterpret_cast<const quad *>(p); }
+
+// Two 64-bit values from one 16-byte unit of a SHARED-memory tile. Written in C++ (a quad load whose halves are then
+// combined into two 64-bit values) the compiler splits the access into two LDS.64; with threads 128 bytes apart under
+// the tile swizzle, or 16 bytes apart in the decoder's column strips, each of those is a 2-way bank conflict — half of
+// all shared-memory wavefronts of the double kernels (profiles/README.md, round 2, item 25). One ld.shared.v2.u64 is
+// one LDS.128: conflict-free for both patterns.
+NDZB_HD void ld_pair64(const uint32_t *p, uint64_t &a, uint64_t &b) {
+#if defined(__CUDA_ARCH__) && !defined(NDZB_SPLIT_LDS64)
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))) : "memory");
+#else
+    const quad q = ld_quad(p);
+    a = (static_cast<uint64_t>(q.y) << 32) | q.x;
+    b = (static_cast<uint64_t>(q.w) << 32) | q.z;
+#endif
+}
 NDZB_HD void st_quad(uint32_t *p, quad q) { *reinterpret_cast<quad *>(p) = q; }
 
 // Input-tile layout of the compress kernel, per profile. A run is two half-runs of 16 values:
@@ -250,9 +265,10 @@ template<typename L>
 NDZB_HD void load_half_rot(const uint32_t *tile, int run, int half, uint64_t *out) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const quad q = ld_quad(tile + L::half_unit(run, half, k));
-        out[2 * k + 0] = rotl1((static_cast<uint64_t>(q.y) << 32) | q.x);
-        out[2 * k + 1] = rotl1((static_cast<uint64_t>(q.w) << 32) | q.z);
+        uint64_t a, b;
+        ld_pair64(tile + L::half_unit(run, half, k), a, b);
+        out[2 * k + 0] = rotl1(a);
+        out[2 * k + 1] = rotl1(b);
     }
 }
 

@@ -1155,9 +1155,7 @@ struct strip {
             s.v[0] = q.x;
             s.v[1] = q.y;
         } else {
-            const quad q = ld_quad(p);
-            s.v[0] = (static_cast<uint64_t>(q.y) << 32) | q.x;
-            s.v[1] = (static_cast<uint64_t>(q.w) << 32) | q.z;
+            ld_pair64(p, s.v[0], s.v[1]);
         }
         return s;
     }
