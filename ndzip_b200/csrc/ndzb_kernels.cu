@@ -621,10 +621,23 @@ constexpr size_t ws_smem_bytes() {
     return static_cast<size_t>(ws_plan<Bits>::slots) * ws_plan<Bits>::slot_bytes + ws_plan<Bits>::aux_bytes;
 }
 
+// one aligned LDS.128 whatever the compiler thinks of the uses of its four words
+__device__ __forceinline__ quad ld_quad_shared(const quad *p) {
+    quad q;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(ptx::smem_addr(p)) : "memory");
+    return q;
+}
+
 // Cube image (shared memory, 1024-byte aligned) -> its place in the stream, by one warp. The destination is only
 // 4-byte aligned; the words up to the first 16-byte boundary and the last < 4 words are stored one by one, the
-// body as aligned 16-byte stores whose four words are picked from two aligned 16-byte shared-memory loads
-// (0.75 instructions per word instead of 2 for a word-by-word copy).
+// body as aligned 16-byte stores whose four words are picked from two adjacent 16-byte units of the image
+// (0.75 instructions per word instead of 2 for a word-by-word copy). The compiler fetches exactly the words it needs
+// — 4- and 8-byte loads 16 bytes apart, i.e. 4- and 2-way bank conflicts, 8 to 12 shared-memory cycles per 512 bytes.
+// -DNDZB_COPY_SHFL is the variant with ONE aligned LDS.128 per lane and the next unit's words by shuffle from the lane
+// above (5 + head cycles per 512 bytes): measured 7-13 % SLOWER on every workload (profiles/r2_copy_shfl_ab.txt) — the
+// copy is a latency chain on a single warp (load -> shuffle -> store, all lanes in lock step), not a bandwidth problem,
+// and the independent loads of this version keep more of them in flight.
+// The image unit behind the last output quad may lie beyond n: it is still inside the slot.
 __device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *dst, uint32_t n, int lane) {
     const uint32_t head = (4u - ((static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst)) >> 2) & 3u)) & 3u;
     if (n < head + 4u) {
@@ -635,6 +648,7 @@ __device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *ds
     const uint32_t nq = (n - head) >> 2;
     const quad *sq = reinterpret_cast<const quad *>(img);
     uint4 *dq = reinterpret_cast<uint4 *>(dst + head);
+#if !defined(NDZB_COPY_SHFL)
     switch (head) {
         case 0:
 #pragma unroll 4
@@ -665,6 +679,58 @@ __device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *ds
             }
             break;
     }
+#else
+    // the loops run the same number of times on every lane (the shuffles need the whole warp)
+    switch (head) {
+        case 0:
+#pragma unroll 4
+            for (uint32_t j = lane; j < nq; j += 32) {
+                const quad a = sq[j];
+                dq[j] = uint4{a.x, a.y, a.z, a.w};
+            }
+            break;
+        case 1:
+#pragma unroll 2
+            for (uint32_t j0 = 0; j0 < nq; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const quad a = ld_quad_shared(sq + j);
+                uint32_t bx = __shfl_down_sync(kFullMask, a.x, 1);
+                if (lane == 31) bx = img[4 * (j + 1)];
+                if (j < nq) dq[j] = uint4{a.y, a.z, a.w, bx};
+            }
+            break;
+        case 2:
+#pragma unroll 2
+            for (uint32_t j0 = 0; j0 < nq; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const quad a = ld_quad_shared(sq + j);
+                uint32_t bx = __shfl_down_sync(kFullMask, a.x, 1), by = __shfl_down_sync(kFullMask, a.y, 1);
+                if (lane == 31) {
+                    const uint2 b = *reinterpret_cast<const uint2 *>(img + 4 * (j + 1));
+                    bx = b.x;
+                    by = b.y;
+                }
+                if (j < nq) dq[j] = uint4{a.z, a.w, bx, by};
+            }
+            break;
+        default:
+#pragma unroll 2
+            for (uint32_t j0 = 0; j0 < nq; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const quad a = ld_quad_shared(sq + j);
+                uint32_t bx = __shfl_down_sync(kFullMask, a.x, 1), by = __shfl_down_sync(kFullMask, a.y, 1),
+                         bz = __shfl_down_sync(kFullMask, a.z, 1);
+                if (lane == 31) {
+                    const quad b = sq[j + 1];
+                    bx = b.x;
+                    by = b.y;
+                    bz = b.z;
+                }
+                if (j < nq) dq[j] = uint4{a.w, bx, by, bz};
+            }
+            break;
+    }
+#endif
     const uint32_t w = head + (nq << 2) + lane;
     if (w < n) dst[w] = img[w];
 }
