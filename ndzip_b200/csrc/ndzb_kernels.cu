@@ -624,7 +624,9 @@ constexpr size_t ws_smem_bytes() {
 // one aligned LDS.128 whatever the compiler thinks of the uses of its four words
 __device__ __forceinline__ quad ld_quad_shared(const quad *p) {
     quad q;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(ptx::smem_addr(p)) : "memory");
+    // volatile (ordered against the mbarrier waits / arrives around the copy, which are volatile too) but WITHOUT a memory
+    // clobber: the global stores of one iteration may sink below the loads of the next
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(ptx::smem_addr(p)));
     return q;
 }
 
@@ -690,7 +692,7 @@ __device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *ds
             }
             break;
         case 1:
-#pragma unroll 2
+#pragma unroll 4
             for (uint32_t j0 = 0; j0 < nq; j0 += 32) {
                 const uint32_t j = j0 + lane;
                 const quad a = ld_quad_shared(sq + j);
@@ -700,7 +702,7 @@ __device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *ds
             }
             break;
         case 2:
-#pragma unroll 2
+#pragma unroll 4
             for (uint32_t j0 = 0; j0 < nq; j0 += 32) {
                 const uint32_t j = j0 + lane;
                 const quad a = ld_quad_shared(sq + j);
@@ -714,7 +716,7 @@ __device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *ds
             }
             break;
         default:
-#pragma unroll 2
+#pragma unroll 4
             for (uint32_t j0 = 0; j0 < nq; j0 += 32) {
                 const uint32_t j = j0 + lane;
                 const quad a = ld_quad_shared(sq + j);
