@@ -405,6 +405,10 @@ chunk_plan plan_chunks(int dims, const uint32_t *size, const grid_geom &g, size_
     for (int d = 1; d < dims; ++d) p.elems_per_cube_row *= size[d];
     const uint64_t row_bytes = p.elems_per_cube_row * elem_bytes;
     uint64_t chunk_bytes = small_first ? kDecompressChunkBytes : kChunkBytes;
+    // small arrays: at least ~8 chunks so that the three streams overlap at all (64 MiB in two 32 MiB chunks is half serial),
+    // but no chunk below 4 MiB (per-chunk launch + event cost)
+    const uint64_t total_bytes = row_bytes * p.cube_rows;
+    if (total_bytes / 8 < chunk_bytes) chunk_bytes = total_bytes / 8 > (uint64_t{4} << 20) ? total_bytes / 8 : (uint64_t{4} << 20);
     if (const char *env = getenv("NDZB_CHUNK_BYTES")) chunk_bytes = strtoull(env, nullptr, 10);  // tests / tuning
     uint64_t rows = chunk_bytes / (row_bytes ? row_bytes : 1);
     if (rows == 0) rows = 1;
