@@ -633,12 +633,13 @@ __device__ __forceinline__ quad ld_quad_shared(const quad *p) {
 // Cube image (shared memory, 1024-byte aligned) -> its place in the stream, by one warp. The destination is only
 // 4-byte aligned; the words up to the first 16-byte boundary and the last < 4 words are stored one by one, the
 // body as aligned 16-byte stores whose four words are picked from two adjacent 16-byte units of the image
-// (0.75 instructions per word instead of 2 for a word-by-word copy). The compiler fetches exactly the words it needs
-// — 4- and 8-byte loads 16 bytes apart, i.e. 4- and 2-way bank conflicts, 8 to 12 shared-memory cycles per 512 bytes.
-// -DNDZB_COPY_SHFL is the variant with ONE aligned LDS.128 per lane and the next unit's words by shuffle from the lane
-// above (5 + head cycles per 512 bytes): measured 7-13 % SLOWER on every workload (profiles/r2_copy_shfl_ab.txt) — the
-// copy is a latency chain on a single warp (load -> shuffle -> store, all lanes in lock step), not a bandwidth problem,
-// and the independent loads of this version keep more of them in flight.
+// (0.75 instructions per word instead of 2 for a word-by-word copy). Both units are loaded whole with a forced
+// ld.shared.v4 (8 conflict-free shared-memory cycles per 512 bytes): left to itself the compiler fetches exactly the
+// words it needs — 4- and 8-byte loads 16 bytes apart, i.e. 4- and 2-way bank conflicts, 8 to 12 cycles
+// (-DNDZB_COPY_NARROW_LOADS; 1-1.5 % slower on 512^3 float, profiles/r2_copy_aligned_ab.txt).
+// -DNDZB_COPY_SHFL is the variant with ONE load per lane and the next unit's words by shuffle from the lane above
+// (5 + head cycles per 512 bytes): 4-13 % SLOWER on every workload (profiles/r2_copy_shfl_ab*.txt) — the copy is a
+// latency chain on a single warp, and load -> shuffle -> store in lock step keeps fewer loads in flight.
 // The image unit behind the last output quad may lie beyond n: it is still inside the slot.
 __device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *dst, uint32_t n, int lane) {
     const uint32_t head = (4u - ((static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst)) >> 2) & 3u)) & 3u;
@@ -651,6 +652,11 @@ __device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *ds
     const quad *sq = reinterpret_cast<const quad *>(img);
     uint4 *dq = reinterpret_cast<uint4 *>(dst + head);
 #if !defined(NDZB_COPY_SHFL)
+#if !defined(NDZB_COPY_NARROW_LOADS)  // two whole 16-byte units per lane, conflict-free (forced: ld.shared.v4)
+#define COPY_LOAD(p) ld_quad_shared(p)
+#else  // plain C++: the compiler fetches only the words it needs, 4- and 8-byte loads 16 bytes apart (bank conflicts)
+#define COPY_LOAD(p) (*(p))
+#endif
     switch (head) {
         case 0:
 #pragma unroll 4
@@ -662,25 +668,26 @@ __device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *ds
         case 1:
 #pragma unroll 4
             for (uint32_t j = lane; j < nq; j += 32) {
-                const quad a = sq[j], b = sq[j + 1];
+                const quad a = COPY_LOAD(sq + j), b = COPY_LOAD(sq + j + 1);
                 dq[j] = uint4{a.y, a.z, a.w, b.x};
             }
             break;
         case 2:
 #pragma unroll 4
             for (uint32_t j = lane; j < nq; j += 32) {
-                const quad a = sq[j], b = sq[j + 1];
+                const quad a = COPY_LOAD(sq + j), b = COPY_LOAD(sq + j + 1);
                 dq[j] = uint4{a.z, a.w, b.x, b.y};
             }
             break;
         default:
 #pragma unroll 4
             for (uint32_t j = lane; j < nq; j += 32) {
-                const quad a = sq[j], b = sq[j + 1];
+                const quad a = COPY_LOAD(sq + j), b = COPY_LOAD(sq + j + 1);
                 dq[j] = uint4{a.w, b.x, b.y, b.z};
             }
             break;
     }
+#undef COPY_LOAD
 #else
     // the loops run the same number of times on every lane (the shuffles need the whole warp)
     switch (head) {
