@@ -779,7 +779,8 @@ int ndzb_bind_host_to_device(int device) {
     cpu_set_t set;
     CPU_ZERO(&set);
     int cpus = 0;
-    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    char *save = nullptr;
+    for (char *tok = strtok_r(list, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {
         int a = 0, b = 0;
         const int n = sscanf(tok, "%d-%d", &a, &b);
         if (n < 1) continue;

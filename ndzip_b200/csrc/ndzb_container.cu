@@ -173,7 +173,7 @@ int ndzb_container_decode_header(const void *buf, uint64_t bytes, ndzb_container
         seg.byte_offset = s[4] | (static_cast<uint64_t>(s[5]) << 32);
         // slabs tile dimension 0 in order; segments are 16-byte aligned, in order, behind the table, without overlap
         if (seg.slab_begin != end_of_previous || seg.slab_end < seg.slab_begin || seg.byte_offset % 16 != 0
-                || seg.byte_offset < end_bytes || seg.stream_words > (1ull << 40)) {
+                || seg.byte_offset < end_bytes || seg.byte_offset > (1ull << 56) || seg.stream_words > (1ull << 40)) {
             return NDZB_ERR_CORRUPT_STREAM;
         }
         end_of_previous = seg.slab_end;
