@@ -91,3 +91,30 @@ def test_argument_errors_mirror_the_reference(lib):
         nz.num_hypercubes((2, 2, 2, 2))                      # reference src/ndzip/common.hh:642
     assert lib.ndzb_strerror(-2).decode().startswith("data dimensionality does not match")
     assert b"sm_100a" in lib.ndzb_version()
+
+
+def test_host_placement_is_a_no_op_without_topology(lib):
+    # ndzb_device_numa_node / ndzb_bind_host_to_device: no CUDA device, or a box that exposes no NUMA node for it
+    # (numa_node = -1, like the pool's VMs): -1 and the calling thread's affinity is left alone
+    import torch
+    import ndzip_b200 as nz
+    before = os.sched_getaffinity(0)
+    if not torch.cuda.is_available():
+        assert nz.device_numa_node(0) == -1 and nz.bind_host_to_device(0) == -1
+        assert os.sched_getaffinity(0) == before
+    assert nz.device_numa_node(10 ** 6) == -1 and nz.bind_host_to_device(10 ** 6) == -1   # no such device
+    assert os.sched_getaffinity(0) == before
+
+
+def test_container_header_arithmetic(lib):
+    # host-only entry points of the sharded container (the data paths are covered in test_dist_cpu.py / container_test.c)
+    from ndzip_b200 import _lib
+    assert lib.ndzb_container_header_bytes(1) == 64 and lib.ndzb_container_header_bytes(2) == 80 and lib.ndzb_container_header_bytes(8) == 224
+    info = _lib.ContainerInfo()
+    dims, sz = _lib.size3((4096 * 4,))
+    assert lib.ndzb_container_plan(0, dims, sz, 4, None, ctypes.byref(info), None) == 0
+    assert info.header_bytes == info.total_bytes == lib.ndzb_container_header_bytes(4) and info.segments == 4
+    assert lib.ndzb_container_plan(0, dims, sz, 0, None, ctypes.byref(info), None) == -1       # no segments
+    assert lib.ndzb_container_plan(2, dims, sz, 4, None, ctypes.byref(info), None) == -1       # bad dtype
+    assert lib.ndzb_container_decode_header(None, 0, ctypes.byref(info), None, 0) == -1
+    assert lib.ndzb_strerror(-7) == b"file input / output failed"
