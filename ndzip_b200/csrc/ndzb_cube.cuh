@@ -365,6 +365,63 @@ NDZB_HD void residual_run(const uint32_t *tile, int u, Bits *r) {
     for (int j = 0; j < 32; ++j) r[j] = complement_negative(r[j]);
 }
 
+// 3-D residuals in two halves around a warp shuffle (compress_ws_kernel, residual_run_3d_warp): residual_run loads five
+// neighbouring half-runs per thread, but two of them (the row above in the own plane and one plane back) only serve to form
+// "row 2p-1 after the z difference" — which the thread of run u-1 holds in the second half of ITS registers once it has
+// taken its own z difference. First half: own run minus the run one plane back. Then the caller hands every thread the
+// second half of run u-1 (__shfl_up_sync by one lane; runs with p = 0 — lanes 0, 8, 16, 24 — have no row above, every other
+// lane's neighbour is in its own warp). Second half: y and x differences, complement. Bit-identical to residual_run.
+// a -= b where cond != 0, as ONE predicated subtraction on the device (the compiler's `if (c) a -= b` is select + subtract)
+NDZB_HD void sub_if(uint32_t &a, uint32_t b, int cond) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q sub.s32 %0, %0, %1;\n\t}" : "+r"(a) : "r"(b), "r"(cond));
+#else
+    if (cond) a -= b;
+#endif
+}
+NDZB_HD void sub_if(uint64_t &a, uint64_t b, int cond) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q sub.s64 %0, %0, %1;\n\t}" : "+l"(a) : "l"(b), "r"(cond));
+#else
+    if (cond) a -= b;
+#endif
+}
+
+template<typename Bits>
+NDZB_HD void residual3_zdiff(const uint32_t *tile, int u, Bits *r) {
+    using L = input_layout<Bits, 3>;
+    Bits *lo = r, *hi = r + 16;
+    load_half_rot<L>(tile, u, 0, lo);
+    load_half_rot<L>(tile, u, 1, hi);
+    const int z = u >> 3;
+    if (z > 0) {
+        Bits back[16];
+        load_half_rot<L>(tile, u - 8, 0, back);
+        sub16(lo, back);
+        load_half_rot<L>(tile, u - 8, 1, back);
+        sub16(hi, back);
+    }
+}
+
+// `above` = r[16..32) of run u-1 after residual3_zdiff (ignored when p == 0)
+template<typename Bits>
+NDZB_HD void residual3_finish(int u, const Bits *above, Bits *r) {
+    Bits *lo = r, *hi = r + 16;
+    const int p = u & 7;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        hi[i] -= lo[i];
+        sub_if(lo[i], above[i], p);
+    }
+#pragma unroll
+    for (int i = 15; i >= 1; --i) {
+        hi[i] -= hi[i - 1];
+        lo[i] -= lo[i - 1];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = complement_negative(r[j]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward: bit planes of a run
 //

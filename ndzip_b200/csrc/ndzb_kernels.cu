@@ -753,42 +753,13 @@ __device__ __forceinline__ void copy_image_out(const uint32_t *img, uint32_t *ds
 // warp. Per thread: 16 instead of 24 LDS.128 (the shuffles cost half the shared-memory cycles of the loads they replace),
 // 64 instead of 96 rotates, 16 subtractions fewer. Bit-identical to residual_run (tests: every 3-D parity case).
 #if !defined(NDZB_NO_SHFL_STENCIL)
-// a -= b where cond != 0, as ONE predicated subtraction (the compiler's version of `if (c) a -= b` is select + subtract)
-__device__ __forceinline__ void sub_if(uint32_t &a, uint32_t b, int cond) {
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q sub.s32 %0, %0, %1;\n\t}" : "+r"(a) : "r"(b), "r"(cond));
-}
-__device__ __forceinline__ void sub_if(uint64_t &a, uint64_t b, int cond) {
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q sub.s64 %0, %0, %1;\n\t}" : "+l"(a) : "l"(b), "r"(cond));
-}
 template<typename Bits>
 __device__ __forceinline__ void residual_run_3d_warp(const uint32_t *tile, int u, Bits *r) {
-    using L = input_layout<Bits, 3>;
-    Bits *lo = r, *hi = r + 16;
-    load_half_rot<L>(tile, u, 0, lo);
-    load_half_rot<L>(tile, u, 1, hi);
-    const int z = u >> 3, p = u & 7;
-    if (z > 0) {
-        Bits back[16];
-        load_half_rot<L>(tile, u - 8, 0, back);
-        sub16(lo, back);
-        load_half_rot<L>(tile, u - 8, 1, back);
-        sub16(hi, back);
-    }
+    residual3_zdiff<Bits>(tile, u, r);  // ndzb_cube.cuh: the two halves are host-callable, tests/host_sim drives them lane by lane
     Bits above[16];  // row 2p-1 of plane z after the z difference: the second row of run u-1
 #pragma unroll
-    for (int i = 0; i < 16; ++i) above[i] = __shfl_up_sync(kFullMask, hi[i], 1);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        hi[i] -= lo[i];
-        sub_if(lo[i], above[i], p);
-    }
-#pragma unroll
-    for (int i = 15; i >= 1; --i) {
-        hi[i] -= hi[i - 1];
-        lo[i] -= lo[i - 1];
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] = complement_negative(r[j]);
+    for (int i = 0; i < 16; ++i) above[i] = __shfl_up_sync(kFullMask, r[16 + i], 1);
+    residual3_finish<Bits>(u, above, r);
 }
 #endif
 

@@ -32,6 +32,20 @@ uint32_t encode_cube(const Bits *cube, Bits *out) {
     // phase 1: residuals (reads the input tile only), heads, plane counts
     std::vector<Bits> res(kCubeElems);
     for (int u = 0; u < kCubeThreads; ++u) residual_run<Bits, Dims>(tile.data(), u, &res[32 * u]);
+    if constexpr (Dims == 3) {
+        // compress_ws_kernel's 3-D path (residual_run_3d_warp): z difference, the second half of run u-1 by
+        // __shfl_up_sync(.., 1) within the warp (lane 0 keeps its own value), then the y / x differences. Must give
+        // exactly what the five-neighbour stencil above gives.
+        std::vector<Bits> warp(kCubeElems), above(16 * kCubeThreads);
+        for (int u = 0; u < kCubeThreads; ++u) residual3_zdiff<Bits>(tile.data(), u, &warp[32 * u]);
+        for (int u = 0; u < kCubeThreads; ++u) {
+            const int src = (u & 31) == 0 ? u : u - 1;
+            memcpy(&above[16 * u], &warp[32 * src + 16], 16 * sizeof(Bits));
+        }
+        for (int u = 0; u < kCubeThreads; ++u) residual3_finish<Bits>(u, &above[16 * u], &warp[32 * u]);
+        if (memcmp(warp.data(), res.data(), kCubeElems * sizeof(Bits)) != 0) return 0;  // no cube compresses to 0 words: the test fails
+        res = warp;
+    }
     Bits heads[tr::chunks];
     for (int c = 0; c < tr::chunks; ++c) heads[c] = 0;
     for (int e = 0; e < kCubeElems; ++e) heads[e / tr::bits] |= res[e];
