@@ -564,6 +564,7 @@ def main():
     torch.cuda.set_device(local_rank)
     # host placement: this rank's thread and the pinned buffers it allocates go to the NUMA node of its GPU
     # (ndzb_bind_host_to_device; -1 = the box exposes no NUMA topology, nothing changed)
+    affinity_before = os.sched_getaffinity(0)
     numa_node = nz.bind_host_to_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -843,6 +844,7 @@ def main():
         line["reference_cuda"] = ref_cuda
     if not args.no_cpu_baseline:
         host = d_in.cpu().numpy()
+        os.sched_setaffinity(0, affinity_before)  # the CPU baseline gets every host core again, not just the GPU's NUMA node
         r = run_cpu_reference(dtype, shape, host, steps=3, warmup=1, threads=0)
         r1 = run_cpu_reference(dtype, shape, host, steps=1, warmup=0, threads=1)
         line["cpu_baseline"] = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"],
