@@ -80,6 +80,13 @@ int ndzb_offload_compress(ndzb_ctx *ctx, const void *h_data, int dims, const uin
 int ndzb_offload_decompress(ndzb_ctx *ctx, const void *h_stream, uint32_t length_words, void *h_data, int dims,
         const uint32_t *size, uint32_t *consumed_words, uint64_t *kernel_ns);
 
+/* How the two calls above cut an array into chunks of whole cube rows along dimension 0 (H2D copies, kernels and D2H
+ * copies of different chunks overlap): *chunks = number of chunks, 0 if the call is not pipelined (border, or below the
+ * size threshold); row_begin (nullable, `capacity` >= *chunks + 1 entries) receives the chunks' first cube rows and, last,
+ * the number of cube rows. Pure host arithmetic (tests, tuning). */
+int ndzb_offload_chunk_plan(int dtype, int dims, const uint32_t *size, int decompress, uint32_t *row_begin, uint32_t capacity,
+        uint32_t *chunks);
+
 /* Page-locked host memory for the buffers handed to the two calls above (the offloader overlaps H2D, kernels
  * and D2H only from pinned memory; pageable buffers work, more slowly). Used by tools/ndzip_compress.cc in place of
  * the reference tool's malloc'ed / mmap'ed chunks (reference src/io/io.cc:23-24, 75-76). */

@@ -21,6 +21,7 @@ SYMBOLS = [
     ("ndzb_decompress", _i, [_vp, _vp, _vp, _i, _vp]),
     ("ndzb_offload_compress", _i, [_vp, _vp, _i, _vp, _vp, _pu32, _pu64]),
     ("ndzb_offload_decompress", _i, [_vp, _vp, _u32, _vp, _i, _vp, _pu32, _pu64]),
+    ("ndzb_offload_chunk_plan", _i, [_i, _i, _vp, _i, _vp, _u32, _pu32]),
     ("ndzb_host_alloc", _i, [ctypes.POINTER(_vp), ctypes.c_size_t]),
     ("ndzb_host_free", None, [_vp]),
     ("ndzb_device_numa_node", _i, [_i]),

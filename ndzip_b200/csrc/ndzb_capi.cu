@@ -733,6 +733,22 @@ int ndzb_ctx_create(ndzb_ctx **out_ctx, int dtype, int dims, uint32_t max_hyperc
     return NDZB_OK;
 }
 
+int ndzb_offload_chunk_plan(int dtype, int dims, const uint32_t *size, int decompress, uint32_t *row_begin, uint32_t capacity, uint32_t *chunks) {
+    if (!valid_profile(dtype, dims) || !size || !chunks) return NDZB_ERR_INVALID_ARGUMENT;
+    const grid_geom g = make_geom(dims, size);
+    *chunks = 0;
+    // the same conditions as ndzb_offload_compress / ndzb_offload_decompress: no border, above the size threshold
+    if (g.num_cubes == 0 || make_border(dims, size).count != 0 || num_elements(dims, size) * word_bytes(dtype) < pipeline_min_bytes()) return NDZB_OK;
+    const chunk_plan plan = plan_chunks(dims, size, g, word_bytes(dtype), decompress != 0);
+    if (plan.chunks <= 1) return NDZB_OK;
+    *chunks = static_cast<uint32_t>(plan.chunks);
+    if (row_begin) {
+        if (capacity < static_cast<uint32_t>(plan.chunks) + 1) return NDZB_ERR_CAPACITY;
+        for (int c = 0; c <= plan.chunks; ++c) row_begin[c] = plan.row_begin[c];
+    }
+    return NDZB_OK;
+}
+
 int ndzb_host_alloc(void **out_ptr, size_t bytes) {
     if (!out_ptr) return NDZB_ERR_INVALID_ARGUMENT;
     *out_ptr = nullptr;

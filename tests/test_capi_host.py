@@ -118,3 +118,47 @@ def test_container_header_arithmetic(lib):
     assert lib.ndzb_container_plan(2, dims, sz, 4, None, ctypes.byref(info), None) == -1       # bad dtype
     assert lib.ndzb_container_decode_header(None, 0, ctypes.byref(info), None, 0) == -1
     assert lib.ndzb_strerror(-7) == b"file input / output failed"
+
+
+def _chunk_plan(lib, dtype, shape, decompress):
+    from ndzip_b200 import _lib
+    dims, sz = _lib.size3(shape)
+    n = ctypes.c_uint32(0)
+    assert lib.ndzb_offload_chunk_plan(dtype, dims, sz, int(decompress), None, 0, ctypes.byref(n)) == 0
+    if n.value == 0:
+        return []
+    rows = (ctypes.c_uint32 * (n.value + 1))()
+    assert lib.ndzb_offload_chunk_plan(dtype, dims, sz, int(decompress), rows, n.value, ctypes.byref(n)) == -3   # capacity: n + 1 entries
+    assert lib.ndzb_offload_chunk_plan(dtype, dims, sz, int(decompress), rows, n.value + 1, ctypes.byref(n)) == 0
+    return list(rows)
+
+
+@pytest.mark.parametrize("decompress", [False, True])
+def test_offloader_chunk_plan_invariants(lib, decompress, monkeypatch):
+    # ndzb_offload_chunk_plan = the plan ndzb_offload_compress / _decompress execute (csrc/ndzb_capi.cu plan_chunks): chunks of whole
+    # cube rows that tile dimension 0 in order, never more than the 128 the per-chunk events / totals are sized for, single-row
+    # pieces at the small end of the pipeline (compression: the back, decompression: the front)
+    side = {1: 4096, 2: 64, 3: 16}
+    cases = [(0, (512, 512, 512)), (1, (8192, 8192)), (1, (128, 1024, 1024)), (0, (1 << 28,)), (0, (1 << 24,)), (0, (1 << 31,)),
+             (1, (1024, 1024, 1024)), (0, (64 * 300, 64 * 40)), (1, (16 * 7, 256, 256)), (0, (4096 * 1025,))]
+    for chunk_env in (None, "4096", str(1 << 20), str(1 << 30)):
+        if chunk_env is None:
+            monkeypatch.delenv("NDZB_CHUNK_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("NDZB_CHUNK_BYTES", chunk_env)
+        for dtype, shape in cases:
+            rows = _chunk_plan(lib, dtype, shape, decompress)
+            cube_rows = shape[0] // side[len(shape)]
+            if not rows:
+                continue
+            lens = [b - a for a, b in zip(rows, rows[1:])]
+            assert rows[0] == 0 and rows[-1] == cube_rows and all(n > 0 for n in lens), (shape, rows)
+            assert 2 <= len(lens) <= 127, (shape, len(lens))
+            small = lens[0] if decompress else lens[-1]
+            assert 2 * small <= max(lens) + 1 or max(lens) == 1, (shape, lens)  # the small end really is small
+    monkeypatch.delenv("NDZB_CHUNK_BYTES", raising=False)
+    # what the headline workload gets: 32 MiB chunks (2 cube rows of 16 MiB), the last one in two pieces
+    assert [b - a for a, b in zip(*(lambda r: (r, r[1:]))(_chunk_plan(lib, 0, (512, 512, 512), False)))] == [2] * 15 + [1, 1]
+    assert [b - a for a, b in zip(*(lambda r: (r, r[1:]))(_chunk_plan(lib, 0, (512, 512, 512), True)))] == [1] * 4 + [4] * 7
+    # not pipelined: a border, or a small array
+    assert _chunk_plan(lib, 0, (513, 512, 512), False) == [] and _chunk_plan(lib, 0, (64, 64, 64), False) == []
